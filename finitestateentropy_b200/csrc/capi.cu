@@ -1,0 +1,419 @@
+// capi.cu -- the C-ABI boundary of libfse_b200.so (declarations: include/fse_b200.h).
+//
+// Two tiers:
+//   1. FSEB200_*_batch : device-pointer, stream-ordered, whole-batch entry points -- what the
+//      per-chunk loops of the reference harness (programs/bench.c:353-364 and :389-424) collapse into.
+//   2. the reference's own one-block-per-call symbols (lib/fse.h, lib/huf.h, lib/hist.h,
+//      lib/fseU16.h) with HOST pointers: they stage the block through a private device workspace and
+//      run the same kernels with a batch of one.  Correct drop-ins for unmodified callers; not the
+//      fast path (one launch + two PCIe copies per call).
+// There is no CPU implementation behind any data-path entry point: without a CUDA device every call
+// aborts loudly.  Only scalar helpers (bounds, error names, table-log arithmetic) run on the host.
+#include "common.cuh"
+#include "micro.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace fseb {
+cudaError_t launch_huf_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t, u32 flags);
+cudaError_t launch_huf_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
+cudaError_t launch_fse_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t);
+cudaError_t launch_fse_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
+cudaError_t launch_fseu16_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t);
+cudaError_t launch_fseu16_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
+cudaError_t launch_hist(const void*, u64, u32, u32*, u64*, cudaStream_t);
+cudaError_t launch_micro(int, const MicroArgs&, void*, u64*, cudaStream_t);
+}
+
+using namespace fseb;
+
+static cudaError_t huf_dec_std(const BatchGeom& g, void* d, const void* c, const u64* cs, u64* r, const void* o, cudaStream_t s) { return launch_huf_decode(g, d, c, cs, r, o, s, 0); }
+static cudaError_t huf_dec_4x1(const BatchGeom& g, void* d, const void* c, const u64* cs, u64* r, const void* o, cudaStream_t s) { return launch_huf_decode(g, d, c, cs, r, o, s, 1); }
+
+#define FSEB_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+[[noreturn]] void die(const char* what, cudaError_t e)
+{
+    std::fprintf(stderr, "libfse_b200: %s failed: %s -- this library has no CPU fallback\n", what, cudaGetErrorString(e));
+    std::abort();
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) die(#call, e_); } while (0)
+
+// Private device workspace of the host-pointer tier.
+struct Workspace {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    unsigned char* d[4] = { nullptr, nullptr, nullptr, nullptr };
+    size_t cap[4] = { 0, 0, 0, 0 };
+    void* get(int i, size_t bytes)
+    {
+        if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        bytes = (bytes + 64 + 255) & ~(size_t)255;          // slack: kernels read whole aligned 16-byte chunks
+        if (cap[i] < bytes) {
+            if (d[i]) CK(cudaFree(d[i]));
+            CK(cudaMalloc(&d[i], bytes));
+            CK(cudaMemset(d[i], 0, bytes));
+            cap[i] = bytes;
+        }
+        return d[i];
+    }
+};
+Workspace& ws() { static Workspace w; return w; }
+
+BatchGeom geom(size_t total, size_t blockSize, size_t slot)
+{
+    BatchGeom g;
+    g.total = total; g.blockSize = (u32)blockSize; g.slot = (u32)slot;
+    g.nBlocks = blockSize ? (u32)((total + blockSize - 1) / blockSize) : 0;
+    return g;
+}
+size_t ok_or_generic(cudaError_t e) { return e == cudaSuccess ? 0 : (size_t)err(E_GENERIC); }
+
+typedef cudaError_t (*enc_fn)(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
+typedef cudaError_t (*dec_fn)(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t);
+
+// one block through the batched encoder; `zeroIsEmpty`: what to answer for srcSize == 0
+size_t one_block_compress(enc_fn fn, void* dst, size_t dstCapacity, const void* src, size_t srcBytes,
+                          unsigned msv, unsigned tlog, bool copyRleByte)
+{
+    Workspace& w = ws();
+    std::lock_guard<std::mutex> lock(w.mu);
+    size_t const cap = dstCapacity > 0xFFFFFF00ull ? 0xFFFFFF00ull : dstCapacity;
+    unsigned char* dS = (unsigned char*)w.get(0, srcBytes);
+    unsigned char* dC = (unsigned char*)w.get(1, cap);
+    u64* dR = (u64*)w.get(2, 2 * sizeof(u64));
+    u64 r = 0;
+    if (srcBytes) CK(cudaMemcpyAsync(dS, src, srcBytes, cudaMemcpyHostToDevice, w.stream));
+    BatchGeom g = geom(srcBytes ? srcBytes : 1, srcBytes ? srcBytes : 1, cap);
+    if (!srcBytes) { g.total = 0; g.nBlocks = 1; }           // a single empty block (bench.c:513,538-544 produces those)
+    CK(fn(g, dC, dR, dS, msv, tlog, w.stream));
+    CK(cudaMemcpyAsync(&r, dR, sizeof(r), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    if (!is_err(r)) {
+        size_t const nOut = (r > 1) ? (size_t)r : ((r == 1 && copyRleByte) ? 1 : 0);
+        if (nOut) { CK(cudaMemcpyAsync(dst, dC, nOut, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); }
+    }
+    return (size_t)r;
+}
+
+size_t one_block_decompress(dec_fn fn, void* dst, size_t dstBytes, const void* cSrc, size_t cSrcSize)
+{
+    Workspace& w = ws();
+    std::lock_guard<std::mutex> lock(w.mu);
+    unsigned char* dC = (unsigned char*)w.get(0, cSrcSize);
+    unsigned char* dO = (unsigned char*)w.get(1, dstBytes);
+    u64* dS = (u64*)w.get(2, 2 * sizeof(u64));
+    u64 hs[2] = { (u64)cSrcSize, 0 };
+    if (cSrcSize) CK(cudaMemcpyAsync(dC, cSrc, cSrcSize, cudaMemcpyHostToDevice, w.stream));
+    CK(cudaMemcpyAsync(dS, hs, sizeof(hs), cudaMemcpyHostToDevice, w.stream));
+    BatchGeom g = geom(dstBytes ? dstBytes : 1, dstBytes ? dstBytes : 1, cSrcSize + 16);
+    if (!dstBytes) { g.total = 0; g.nBlocks = 1; }
+    CK(fn(g, dO, dC, dS, dS + 1, nullptr, w.stream));
+    CK(cudaMemcpyAsync(hs, dS, sizeof(hs), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    if (!is_err(hs[1]) && hs[1]) {
+        size_t const nOut = hs[1] < dstBytes ? (size_t)hs[1] : dstBytes;
+        CK(cudaMemcpyAsync(dst, dO, nOut, cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaStreamSynchronize(w.stream));
+    }
+    return (size_t)hs[1];
+}
+
+// runs one table-level op: uploads `in` at offset 0 of the scratch, returns the kernel's value; the
+// caller then downloads what it needs from the scratch.
+struct Micro {
+    Workspace& w; unsigned char* buf; u64* ret; std::unique_lock<std::mutex> lock;
+    Micro() : w(ws()), lock(w.mu) { buf = (unsigned char*)w.get(3, 256 * 1024); ret = (u64*)w.get(2, 2 * sizeof(u64)); }
+    void up(size_t off, const void* p, size_t n) { if (n) CK(cudaMemcpyAsync(buf + off, p, n, cudaMemcpyHostToDevice, w.stream)); }
+    void down(void* p, size_t off, size_t n) { if (n) { CK(cudaMemcpyAsync(p, buf + off, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); } }
+    u64 run(int op, u64 a0 = 0, u64 a1 = 0, u64 a2 = 0, u64 a3 = 0)
+    {
+        MicroArgs A; A.a[0] = a0; A.a[1] = a1; A.a[2] = a2; A.a[3] = a3; A.a[4] = A.a[5] = 0;
+        u64 r = 0;
+        CK(launch_micro(op, A, buf, ret, w.stream));
+        CK(cudaMemcpyAsync(&r, ret, sizeof(r), cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaStreamSynchronize(w.stream));
+        return r;
+    }
+};
+
+unsigned hibit_h(unsigned v) { unsigned r = 0; while (v >>= 1) r++; return r; }
+
+}  // namespace
+
+// ================================================================================================
+// tier 1: batched, device-resident.  Geometry: programs/bench.c:530-548 (see common.cuh BatchGeom).
+// ================================================================================================
+#define FSEB_DECL_DEC(NAME, FN, MAXBLOCK) \
+FSEB_API size_t NAME(void* dDst, size_t dstTotal, size_t blockSize, const void* dCBuf, size_t slot, \
+                     const size_t* dCSizes, size_t* dResults, const void* dOrig, void* stream) \
+{ \
+    if (blockSize == 0 || blockSize > (MAXBLOCK) || slot > 0xFFFFFFFFull) return (size_t)err(E_SRC_WRONG); \
+    return ok_or_generic(FN(geom(dstTotal, blockSize, slot), dDst, dCBuf, (const u64*)dCSizes, (u64*)dResults, dOrig, (cudaStream_t)stream)); \
+}
+#define FSEB_DECL_ENC(NAME, FN, MAXBLOCK) \
+FSEB_API size_t NAME(void* dCBuf, size_t slot, size_t* dCSizes, const void* dSrc, size_t srcTotal, size_t blockSize, \
+                     unsigned maxSymbolValue, unsigned tableLog, void* stream) \
+{ \
+    if (blockSize == 0 || blockSize > (MAXBLOCK) || slot > 0xFFFFFFFFull) return (size_t)err(E_SRC_WRONG); \
+    return ok_or_generic(FN(geom(srcTotal, blockSize, slot), dCBuf, (u64*)dCSizes, dSrc, maxSymbolValue, tableLog, (cudaStream_t)stream)); \
+}
+FSEB_DECL_DEC(FSEB200_HUF_decompress_batch, huf_dec_std, HUF_BLOCK_MAX)
+FSEB_DECL_ENC(FSEB200_HUF_compress_batch, launch_huf_encode, HUF_BLOCK_MAX)
+FSEB_DECL_DEC(FSEB200_FSE_decompress_batch, launch_fse_decode, (1u << 30))
+FSEB_DECL_ENC(FSEB200_FSE_compress_batch, launch_fse_encode, (1u << 30))
+FSEB_DECL_DEC(FSEB200_FSEU16_decompress_batch, launch_fseu16_decode, (1u << 30))
+FSEB_DECL_ENC(FSEB200_FSEU16_compress_batch, launch_fseu16_encode, (1u << 30))
+
+FSEB_API size_t FSEB200_batch_blocks(size_t total, size_t blockSize) { return blockSize ? (total + blockSize - 1) / blockSize : 0; }
+FSEB_API int FSEB200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+
+// ================================================================================================
+// tier 2a: scalar helpers (host arithmetic only)
+// ================================================================================================
+FSEB_API unsigned FSE_versionNumber(void) { return 0 * 10000 + 9 * 100 + 0; }                 // lib/fse.h:43-47
+FSEB_API size_t FSE_compressBound(size_t size) { return 512 + size + (size >> 7) + 4 + sizeof(size_t); }   // lib/fse.h:290-292
+FSEB_API size_t HUF_compressBound(size_t size) { return 129 + size + (size >> 8) + 8; }       // lib/huf.h:131-133
+FSEB_API unsigned FSE_isError(size_t code) { return code > (size_t)err(E_MAXCODE); }          // lib/error_private.h:79
+FSEB_API unsigned HUF_isError(size_t code) { return FSE_isError(code); }
+FSEB_API unsigned HIST_isError(size_t code) { return FSE_isError(code); }
+FSEB_API const char* FSE_getErrorName(size_t code)                                             // lib/error_private.h:92-117
+{
+    if (!FSE_isError(code)) return "No error detected";
+    switch ((unsigned)(0 - code)) {
+    case E_GENERIC: return "Error (generic)";
+    case E_DST_TOO_SMALL: return "Destination buffer is too small";
+    case E_SRC_WRONG: return "Src size is incorrect";
+    case E_CORRUPT: return "Corrupted block detected";
+    case E_TLOG_TOO_LARGE: return "tableLog requires too much memory : unsupported";
+    case E_MSV_TOO_LARGE: return "Unsupported max Symbol Value : too large";
+    case E_MSV_TOO_SMALL: return "Specified maxSymbolValue is too small";
+    case E_WKSP_TOO_SMALL: return "workspace buffer is too small";
+    default: return "Unspecified error code";
+    }
+}
+FSEB_API const char* HUF_getErrorName(size_t code) { return FSE_getErrorName(code); }
+
+static unsigned optimal_tablelog_h(unsigned maxTableLog, size_t srcSize, unsigned msv, unsigned minus)   // lib/fse_compress.c:316-342
+{
+    unsigned const bySrc = hibit_h((unsigned)(srcSize - 1)) - minus;
+    unsigned const a = hibit_h((unsigned)srcSize) + 1, b = hibit_h(msv) + 2;
+    unsigned const floorBits = a < b ? a : b;
+    unsigned tl = maxTableLog ? maxTableLog : FSE_DEF_TLOG;
+    if (bySrc < tl) tl = bySrc;
+    if (floorBits > tl) tl = floorBits;
+    if (tl < FSE_MIN_TLOG) tl = FSE_MIN_TLOG;
+    if (tl > FSE_MAX_TLOG) tl = FSE_MAX_TLOG;
+    return tl;
+}
+FSEB_API unsigned FSE_optimalTableLog(unsigned maxTableLog, size_t srcSize, unsigned msv) { return optimal_tablelog_h(maxTableLog, srcSize, msv, 2); }
+FSEB_API unsigned FSE_optimalTableLog_internal(unsigned maxTableLog, size_t srcSize, unsigned msv, unsigned minus) { return optimal_tablelog_h(maxTableLog, srcSize, msv, minus); }
+FSEB_API unsigned HUF_optimalTableLog(unsigned maxTableLog, size_t srcSize, unsigned msv) { return optimal_tablelog_h(maxTableLog, srcSize, msv, 1); }
+FSEB_API size_t FSE_NCountWriteBound(unsigned msv, unsigned tl) { return msv ? (((size_t)(msv + 1) * tl) >> 3) + 3 : 512; }   // lib/fse_compress.c:186-190
+
+FSEB_API unsigned HUF_selectDecoder(size_t dstSize, size_t cSrcSize)                            // lib/huf_decompress.c:1001-1051
+{
+    static const unsigned short cost[16][4] = {
+        {0, 0, 1, 1}, {0, 0, 1, 1}, {38, 130, 1313, 74}, {448, 128, 1353, 74}, {556, 128, 1353, 74},
+        {714, 128, 1418, 74}, {883, 128, 1437, 74}, {897, 128, 1515, 75}, {926, 128, 1613, 75},
+        {947, 128, 1729, 77}, {1107, 128, 2083, 81}, {1177, 128, 2379, 87}, {1242, 128, 2415, 93},
+        {1349, 128, 2644, 106}, {1455, 128, 2422, 124}, {722, 128, 1891, 145} };
+    unsigned const q = (cSrcSize >= dstSize) ? 15 : (unsigned)(cSrcSize * 16 / dstSize);
+    unsigned const d256 = (unsigned)(dstSize >> 8);
+    unsigned const t0 = cost[q][0] + cost[q][1] * d256;
+    unsigned t1 = cost[q][2] + cost[q][3] * d256;
+    t1 += t1 >> 3;
+    return t1 < t0;
+}
+
+FSEB_API unsigned* FSE_createCTable(unsigned msv, unsigned tl)                                  // lib/fse_compress.c:305-312
+{ if (tl > FSE_ABS_TLOG) tl = FSE_ABS_TLOG; return (unsigned*)std::malloc((1 + ((size_t)1 << (tl - 1)) + ((size_t)msv + 1) * 2) * sizeof(unsigned)); }
+FSEB_API void FSE_freeCTable(unsigned* ct) { std::free(ct); }
+FSEB_API unsigned* FSE_createDTable(unsigned tl)                                                // lib/fse_decompress.c:57-66
+{ if (tl > FSE_ABS_TLOG) tl = FSE_ABS_TLOG; return (unsigned*)std::malloc((1 + ((size_t)1 << tl)) * sizeof(unsigned)); }
+FSEB_API void FSE_freeDTable(unsigned* dt) { std::free(dt); }
+
+// ================================================================================================
+// tier 2b: one block per call, host pointers
+// ================================================================================================
+FSEB_API size_t FSE_compress2(void* dst, size_t cap, const void* src, size_t n, unsigned msv, unsigned tl)     // lib/fse.h:105
+{ return one_block_compress(launch_fse_encode, dst, cap, src, n, msv, tl, false); }
+FSEB_API size_t FSE_compress(void* dst, size_t cap, const void* src, size_t n)                                    // lib/fse.h:67 -> (255, 11)
+{ return FSE_compress2(dst, cap, src, n, FSE_MAX_SV, FSE_DEF_TLOG); }
+FSEB_API size_t FSE_decompress(void* dst, size_t cap, const void* cSrc, size_t cSize)                             // lib/fse.h:80
+{ return one_block_decompress(launch_fse_decode, dst, cap, cSrc, cSize); }
+
+FSEB_API size_t HUF_compress2(void* dst, size_t cap, const void* src, size_t n, unsigned msv, unsigned tl)      // lib/huf.h:86
+{
+    if (!n) return 0;                                                   // huf_compress.c:656
+    if (!cap) return 0;
+    if (n > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
+    return one_block_compress(launch_huf_encode, dst, cap, src, n, msv, tl, true);
+}
+FSEB_API size_t HUF_compress(void* dst, size_t cap, const void* src, size_t n) { return HUF_compress2(dst, cap, src, n, 255, HUF_DEF_TLOG); }   // lib/huf.h:54
+FSEB_API size_t HUF_compress4X_wksp(void* dst, size_t cap, const void* src, size_t n, unsigned msv, unsigned tl, void* wksp, size_t wkspSize)
+{
+    if (((size_t)wksp & 3) != 0) return (size_t)err(E_GENERIC);        // huf_compress.c:652-653
+    if (wkspSize < (6 << 10)) return (size_t)err(E_WKSP_TOO_SMALL);
+    return HUF_compress2(dst, cap, src, n, msv, tl);
+}
+FSEB_API size_t HUF_decompress(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                     // lib/huf.h:67
+{
+    if (dstSize == 0) return (size_t)err(E_DST_TOO_SMALL);
+    if (dstSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);      // kernels are sized for HUF_BLOCKSIZE_MAX (lib/huf.h:72)
+    return one_block_decompress(huf_dec_std, dst, dstSize, cSrc, cSrcSize);
+}
+// Both produce identical bytes for valid input; the GPU path has a single decoder.
+FSEB_API size_t HUF_decompress4X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                  // lib/huf.h:155
+{
+    if (dstSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
+    return one_block_decompress(huf_dec_4x1, dst, dstSize, cSrc, cSrcSize);   // never treats the input as raw / RLE (huf_decompress.c:416-449)
+}
+FSEB_API size_t HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize) { return HUF_decompress4X1(dst, dstSize, cSrc, cSrcSize); }
+
+FSEB_API size_t FSE_compressU16(void* dst, size_t cap, const unsigned short* src, size_t n, unsigned msv, unsigned tl)   // lib/fseU16.h:75
+{
+    if (n <= 1) return n;
+    return one_block_compress(launch_fseu16_encode, dst, cap, src, n * 2, msv, tl, false);
+}
+FSEB_API size_t FSE_decompressU16(unsigned short* dst, size_t cap, const void* cSrc, size_t cSize)                 // lib/fseU16.h:79
+{
+    if (cSize < 2) return (size_t)err(E_SRC_WRONG);
+    size_t const r = one_block_decompress(launch_fseu16_decode, dst, cap * 2, cSrc, cSize);
+    return FSE_isError(r) ? r : r / 2;
+}
+
+// ================================================================================================
+// tier 2c: statistics and tables, host pointers (single-CTA kernels, micro.cu)
+// ================================================================================================
+FSEB_API size_t HIST_count(unsigned* count, unsigned* msvPtr, const void* src, size_t n)                          // lib/hist.h:30
+{
+    Workspace& w = ws();
+    std::lock_guard<std::mutex> lock(w.mu);
+    unsigned char* dS = (unsigned char*)w.get(0, n);
+    u32* dOut = (u32*)w.get(1, 260 * sizeof(u32));
+    u64* dR = (u64*)w.get(2, 2 * sizeof(u64));
+    unsigned const declared = *msvPtr > 255 ? 255 : *msvPtr;
+    u32 out[257]; u64 r = 0;
+    if (n) CK(cudaMemcpyAsync(dS, src, n, cudaMemcpyHostToDevice, w.stream));
+    CK(launch_hist(dS, n, declared, dOut, dR, w.stream));
+    CK(cudaMemcpyAsync(&r, dR, sizeof(r), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaMemcpyAsync(out, dOut, sizeof(out), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    if (is_err(r)) return (size_t)r;
+    std::memcpy(count, out, (declared + 1) * sizeof(unsigned));
+    *msvPtr = out[256];
+    return (size_t)r;
+}
+FSEB_API size_t HIST_countFast(unsigned* count, unsigned* msvPtr, const void* src, size_t n) { return HIST_count(count, msvPtr, src, n); }
+FSEB_API unsigned HIST_count_simple(unsigned* count, unsigned* msvPtr, const void* src, size_t n) { return (unsigned)HIST_count(count, msvPtr, src, n); }
+FSEB_API size_t HIST_count_wksp(unsigned* count, unsigned* msvPtr, const void* src, size_t n, void* wksp, size_t wkspSize)
+{
+    if ((size_t)wksp & 3) return (size_t)err(E_GENERIC);                // hist.c:167-168
+    if (wkspSize < 1024 * sizeof(unsigned)) return (size_t)err(E_WKSP_TOO_SMALL);
+    return HIST_count(count, msvPtr, src, n);
+}
+FSEB_API size_t HIST_countFast_wksp(unsigned* count, unsigned* msvPtr, const void* src, size_t n, void* wksp, size_t wkspSize)
+{ return HIST_count_wksp(count, msvPtr, src, n, wksp, wkspSize); }
+
+FSEB_API size_t FSE_normalizeCount(short* norm, unsigned tl, const unsigned* count, size_t total, unsigned msv)   // lib/fse.h:147
+{
+    if (msv > 4095) return (size_t)err(E_MSV_TOO_LARGE);
+    Micro m; m.up(0, count, (msv + 1) * sizeof(unsigned));
+    u64 const r = m.run(MOP_NORMALIZE, tl, total, msv);
+    if (!is_err(r)) m.down(norm, 4096, (msv + 1) * sizeof(short));
+    return (size_t)r;
+}
+FSEB_API size_t FSE_writeNCount(void* buffer, size_t bufferSize, const short* norm, unsigned msv, unsigned tl)     // lib/fse.h:157
+{
+    if (msv > 1023) return (size_t)err(E_MSV_TOO_LARGE);
+    Micro m; m.up(0, norm, (msv + 1) * sizeof(short));
+    size_t const cap = bufferSize > 60000 ? 60000 : bufferSize;
+    u64 const r = m.run(MOP_WRITE_NCOUNT, cap, msv, tl);
+    if (!is_err(r)) m.down(buffer, 4096, (size_t)r);
+    return (size_t)r;
+}
+FSEB_API size_t FSE_readNCount(short* norm, unsigned* msvPtr, unsigned* tlPtr, const void* hdr, size_t hbSize)     // lib/fse.h:227
+{
+    if (*msvPtr > 1023) return (size_t)err(E_MSV_TOO_LARGE);
+    Micro m;
+    size_t const take = hbSize > 4000 ? 4000 : hbSize;                  // a header never exceeds FSE_NCOUNTBOUND (512)
+    m.up(0, hdr, take);
+    u64 const r = m.run(MOP_READ_NCOUNT, take, *msvPtr);
+    unsigned const declared = *msvPtr;
+    unsigned meta[2] = { 0, 0 };
+    m.down(meta, 8192, sizeof(meta));
+    *tlPtr = meta[1];
+    if (is_err(r)) { m.down(norm, 4096, (declared + 1) * sizeof(short)); return (size_t)r; }
+    m.down(norm, 4096, (declared + 1) * sizeof(short));
+    *msvPtr = meta[0];
+    return (size_t)r;
+}
+FSEB_API size_t FSE_buildCTable(unsigned* ct, const short* norm, unsigned msv, unsigned tl)                          // lib/fse.h:163
+{
+    if (msv > FSE_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    Micro m; m.up(0, norm, (msv + 1) * sizeof(short));
+    u64 const r = m.run(MOP_BUILD_CTABLE, msv, tl);
+    if (!is_err(r)) m.down(ct, 4096, (1 + (tl ? ((size_t)1 << (tl - 1)) : 1) + ((size_t)msv + 1) * 2) * sizeof(unsigned));
+    return (size_t)r;
+}
+FSEB_API size_t FSE_buildDTable(unsigned* dt, const short* norm, unsigned msv, unsigned tl)                          // lib/fse.h:240
+{
+    if (msv > FSE_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    if (tl > FSE_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    Micro m; m.up(0, norm, (msv + 1) * sizeof(short));
+    u64 const r = m.run(MOP_BUILD_DTABLE, msv, tl, 0);
+    if (!is_err(r)) m.down(dt, 4096, (1 + ((size_t)1 << tl)) * sizeof(unsigned));
+    return (size_t)r;
+}
+FSEB_API size_t HUF_buildCTable(unsigned* ctable, const unsigned* count, unsigned msv, unsigned maxNbBits)            // lib/huf.h:188
+{
+    if (msv > HUF_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    unsigned cnt[256];
+    std::memcpy(cnt, count, (msv + 1) * sizeof(unsigned));             // CTable and count may overlap (huf.h:188 note)
+    Micro m; m.up(0, cnt, (msv + 1) * sizeof(unsigned));
+    u64 const r = m.run(MOP_HUF_BUILD_CTABLE, msv, maxNbBits);
+    if (!is_err(r)) m.down(ctable, 4096, (msv + 1) * sizeof(unsigned));
+    return (size_t)r;
+}
+FSEB_API size_t HUF_writeCTable(void* dst, size_t maxDstSize, const unsigned* ctable, unsigned msv, unsigned huffLog)  // lib/huf.h:189
+{
+    if (msv > HUF_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    Micro m; m.up(0, ctable, (msv + 1) * sizeof(unsigned));
+    u64 const r = m.run(MOP_HUF_WRITE_CTABLE, maxDstSize, msv, huffLog);
+    if (!is_err(r)) m.down(dst, 4096, (size_t)r);
+    return (size_t)r;
+}
+FSEB_API size_t HUF_readStats(unsigned char* huffWeight, size_t hwSize, unsigned* rankStats, unsigned* nbSymbolsPtr,
+                              unsigned* tableLogPtr, const void* src, size_t srcSize)                                   // lib/huf.h:225
+{
+    if (hwSize > 4000) hwSize = 4000;
+    Micro m;
+    size_t const take = srcSize > 256 ? 256 : srcSize;                  // a tree header never exceeds HUF_CTABLEBOUND (129)
+    m.up(0, src, take);
+    u64 const r = m.run(MOP_HUF_READ_STATS, take, hwSize);
+    if (is_err(r)) return (size_t)r;
+    unsigned meta[2];
+    m.down(meta, 8192 + 64, sizeof(meta));
+    m.down(rankStats, 8192, 13 * sizeof(unsigned));
+    m.down(huffWeight, 4096, meta[0]);
+    *nbSymbolsPtr = meta[0]; *tableLogPtr = meta[1];
+    return (size_t)r;
+}
+FSEB_API size_t HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSize)                                    // lib/huf.h:267
+{
+    Micro m;
+    size_t const take = srcSize > 256 ? 256 : srcSize;
+    m.up(0, src, take);
+    u64 const r = m.run(MOP_HUF_READ_DTABLE_X1, take, DTable[0]);
+    if (is_err(r)) return (size_t)r;
+    unsigned hdr = 0;
+    m.down(&hdr, 16384, sizeof(hdr));
+    unsigned const tl = (hdr >> 16) & 0xFF;
+    m.down(DTable, 16384, sizeof(unsigned) + ((size_t)1 << tl) * 2);
+    return (size_t)r;
+}

@@ -1,0 +1,271 @@
+"""Parity of every CUDA codec path against the CPU checker through the C-ABI (-m gpu):
+identical compressed bytes and return values (incl. the in-band 0 / 1), both cross-decodes,
+golden vectors, table images, and the size-independent round-trip property at larger sizes."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ptr, zoo, rand_size, probagen, gen_u16, is_error
+from gpu_common import cpu_compress, cpu_decompress, checker, BLOCK, SLOT
+import finitestateentropy_b200 as fb
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+U = C.c_uint
+
+
+def _dev(a):
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.uint8)).cuda()
+
+
+ENC = {"huf": fb.huf_compress_batch, "fse": fb.fse_compress_batch, "u16": fb.fseu16_compress_batch}
+DEC = {"huf": fb.huf_decompress_batch, "fse": fb.fse_decompress_batch, "u16": fb.fseu16_decompress_batch}
+
+
+def _roundtrip_vs_checker(codec, data, block, msv=255, tl=12, slot=None):
+    data = np.ascontiguousarray(data).view(np.uint8)
+    slot = slot or (32768 if codec == "u16" and block == 32768 else 512 + block + (block >> 7) + 12)
+    want_c, want_cs, _ = cpu_compress(codec, data, block=block, slot=slot, msv=msv, tl=tl)
+    d_src = _dev(data)
+    cbuf, cs = ENC[codec](d_src, block, slot, msv, tl)
+    torch.cuda.synchronize()
+    got_cs = cs.cpu().numpy().view(np.uint64)
+    got_c = cbuf.cpu().numpy()
+    nb = len(want_cs)
+    for b in range(nb):
+        assert got_cs[b] == want_cs[b], (codec, block, b, int(got_cs[b]), int(want_cs[b]))
+        if not is_error(int(want_cs[b])) and want_cs[b] > 1:
+            a = got_c[b * slot: b * slot + int(want_cs[b])]; w = want_c[b * slot: b * slot + int(want_cs[b])]
+            assert np.array_equal(a, w), (codec, block, b, int(np.nonzero(a != w)[0][0]))
+        if codec == "huf" and want_cs[b] == 1:
+            assert got_c[b * slot] == want_c[b * slot]
+    # GPU decode of GPU output, CPU decode of GPU output
+    want_out, want_res = cpu_decompress(codec, got_c, got_cs.copy(), data, block=block, slot=slot)
+    out, res = DEC[codec](cbuf, cs, len(data), block, slot, orig=d_src)
+    torch.cuda.synchronize()
+    res = res.cpu().numpy().view(np.uint64); out = out.cpu().numpy()
+    for b in range(nb):
+        if is_error(int(got_cs[b])):
+            continue
+        assert res[b] == want_res[b], (codec, block, b, int(res[b]), int(want_res[b]), int(got_cs[b]))
+        n = min(block, len(data) - b * block)
+        if not is_error(int(want_res[b])):
+            assert np.array_equal(out[b * block: b * block + n], data[b * block: b * block + n]), (codec, b)
+    return got_cs
+
+
+@pytest.mark.parametrize("codec,p", [("huf", 0.14), ("huf", 0.80), ("huf", 0.02), ("fse", 0.20), ("fse", 0.80), ("fse", 0.02), ("fse", 0.14)])
+def test_probagen_1mib_matches_kat(codec, p):
+    """config[0]-style run: 1,048,575 B, 32 blocks, (255,12) -- totals must match SURVEY.md 6.3 / kat_bench.json"""
+    data = probagen(1048575, p)
+    cs = _roundtrip_vs_checker(codec, data, BLOCK, slot=SLOT)
+    kat = {(r["name"], r["codec"]): r for r in json.load(open(os.path.join(HERE, "golden", "kat_bench.json")))}
+    rec = kat[("proba%02d" % round(p * 100), codec)]
+    assert [int(x) for x in cs] == rec["cSizes"]
+
+
+def test_u16_matches_kat():
+    data = gen_u16(524288, 240, 0.50, 1)
+    cs = _roundtrip_vs_checker("u16", data, 32768, msv=0, tl=12, slot=32768)
+    rec = [r for r in json.load(open(os.path.join(HERE, "golden", "kat_bench.json"))) if r["codec"] == "u16"][0]
+    assert [int(x) for x in cs] == rec["cSizes"]
+
+
+@pytest.mark.parametrize("codec", ["huf", "fse"])
+def test_zoo_blocks(codec):
+    rng = np.random.default_rng(21 if codec == "huf" else 22)
+    for block in (32768, 4099, 1000, 65536, 131072, 12, 77, 13):
+        parts = [zoo(rng, block) for _ in range(int(rng.integers(3, 40)))]
+        parts.append(zoo(rng, int(rng.integers(1, block + 1))))
+        _roundtrip_vs_checker(codec, np.concatenate(parts), block)
+
+
+def test_u16_zoo():
+    rng = np.random.default_rng(23)
+    for block_syms in (16384, 1000, 4099, 3, 2):
+        parts = []
+        for _ in range(12):
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                parts.append(gen_u16(block_syms, 240, float(rng.uniform(0.05, 0.9)), int(rng.integers(1, 1 << 30))))
+            elif k == 1:
+                parts.append(rng.integers(0, int(rng.integers(1, 287)), block_syms).astype(np.uint16))
+            else:
+                parts.append(np.full(block_syms, int(rng.integers(0, 287)), np.uint16))
+        data = np.concatenate(parts)
+        _roundtrip_vs_checker("u16", data, 2 * block_syms, msv=0, tl=12, slot=2 * block_syms + 600)
+
+
+def test_golden_small_vectors_through_host_api():
+    """tests/golden/vectors_small.npz through the reference-named one-block entry points (host pointers)"""
+    L = fb.lib()
+    for name, res, args in (("FSE_compress2", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, U, U]),
+                            ("HUF_compress2", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, U, U]),
+                            ("FSE_compressU16", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, U, U]),
+                            ("FSE_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+                            ("HUF_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+                            ("FSE_decompressU16", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t])):
+        f = getattr(L, name); f.restype = res; f.argtypes = args
+    z = np.load(os.path.join(HERE, "golden", "vectors_small.npz"))
+    for k in range(int(z["count"][0])):
+        d = np.ascontiguousarray(z["in_%d" % k]); codec = int(z["codec_%d" % k][0])
+        want = int(z["ret_%d" % k][0]); wout = z["out_%d" % k]
+        n = len(d)
+        if codec == 2:
+            dst = np.zeros(n + 600, np.uint8)
+            r = L.FSE_compressU16(ptr(dst), n + 592, ptr(d), n // 2, 0, 12)
+        else:
+            cap = 512 + n + (n >> 7) + 12
+            dst = np.zeros(cap + 8, np.uint8)
+            r = (L.FSE_compress2 if codec == 0 else L.HUF_compress2)(ptr(dst), cap, ptr(d), n, 255, 12)
+        assert r == want, (k, codec, n, r, want)
+        if not is_error(r) and r > 1:
+            assert bytes(dst[:r]) == bytes(wout), (k, codec, n)
+            out = np.zeros(n + 2, np.uint8)
+            if codec == 2:
+                assert L.FSE_decompressU16(ptr(out), n // 2, ptr(dst), r) == n // 2
+                assert np.array_equal(out[:n], d)
+            else:
+                dr = (L.FSE_decompress if codec == 0 else L.HUF_decompress)(ptr(out), n, ptr(dst), r)
+                if not is_error(dr):
+                    assert dr == n and np.array_equal(out[:n], d)
+
+
+def test_fse_error_verdicts():
+    """truncated / corrupted FSE blocks: same verdict and bytes as the CPU decoder (programs/fuzzer.c:253-262)"""
+    lib, isref = checker()
+    dec = lib.FSE_decompress if isref else lib.orc_fse_decompress
+    rng = np.random.default_rng(24)
+    block = 4096
+    data = np.concatenate([zoo(rng, block) for _ in range(120)])
+    cbuf, cs, slot = cpu_compress("fse", data, block=block)
+    nb = len(cs); want = np.zeros(nb, np.uint64); wout = np.zeros(len(data), np.uint8)
+    for b in range(nb):
+        if cs[b] < 2:
+            want[b] = block; wout[b * block:(b + 1) * block] = data[b * block:(b + 1) * block]
+            continue
+        c = cbuf[b * slot: b * slot + int(cs[b])]
+        mode = int(rng.integers(0, 3))
+        if mode == 0:
+            cs[b] = int(rng.integers(2, int(cs[b])))
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                c[int(rng.integers(0, len(c)))] ^= int(rng.integers(1, 256))
+        tmp = np.concatenate([cbuf[b * slot: b * slot + int(cs[b])], np.zeros(32, np.uint8)])
+        o = np.zeros(block + 8, np.uint8)
+        want[b] = dec(ptr(o), block, ptr(tmp), int(cs[b]))
+        wout[b * block:(b + 1) * block] = o[:block]
+    guard = torch.full((len(data) + 4096,), 0x5A, dtype=torch.uint8, device="cuda")
+    out, res = fb.fse_decompress_batch(_dev(cbuf), _dev(cs), len(data), block, slot, out=guard, orig=_dev(data))
+    torch.cuda.synchronize()
+    res = res.cpu().numpy().view(np.uint64); out = out.cpu().numpy()
+    bad = [(b, int(res[b]), int(want[b])) for b in range(nb) if res[b] != want[b]]
+    assert not bad, bad[:10]
+    for b in range(nb):
+        if not is_error(int(want[b])):
+            k = int(want[b])
+            assert np.array_equal(out[b * block: b * block + k], wout[b * block: b * block + k]), b
+    assert (guard[len(data):] == 0x5A).all()
+    assert sum(is_error(int(x)) for x in want) > 5
+
+
+def test_table_level_api_images():
+    """HIST_count / FSE_normalizeCount / NCount / FSE_buildCTable / FSE_buildDTable / HUF_buildCTable /
+    HUF_writeCTable / HUF_readStats / HUF_readDTableX1 computed on the GPU vs the CPU checker's images"""
+    lib, isref = checker()
+    if not isref:
+        pytest.skip("table images are compared against the compiled reference only")
+    L = fb.lib()
+    P = C.POINTER
+    def sig(n, *a):
+        f = getattr(L, n); f.restype = C.c_size_t; f.argtypes = list(a); return f
+    g_hist = sig("HIST_count", P(U), P(U), C.c_void_p, C.c_size_t)
+    g_norm = sig("FSE_normalizeCount", P(C.c_short), U, P(U), C.c_size_t, U)
+    g_wn = sig("FSE_writeNCount", C.c_void_p, C.c_size_t, P(C.c_short), U, U)
+    g_rn = sig("FSE_readNCount", P(C.c_short), P(U), P(U), C.c_void_p, C.c_size_t)
+    g_ct = sig("FSE_buildCTable", C.c_void_p, P(C.c_short), U, U)
+    g_dt = sig("FSE_buildDTable", C.c_void_p, P(C.c_short), U, U)
+    g_hct = sig("HUF_buildCTable", C.c_void_p, P(U), U, U)
+    g_hw = sig("HUF_writeCTable", C.c_void_p, C.c_size_t, C.c_void_p, U, U)
+    g_hrs = sig("HUF_readStats", C.c_void_p, C.c_size_t, P(C.c_uint32), P(C.c_uint32), P(C.c_uint32), C.c_void_p, C.c_size_t)
+    g_hdt = sig("HUF_readDTableX1", C.c_void_p, C.c_void_p, C.c_size_t)
+    L.FSE_optimalTableLog.argtypes = [U, C.c_size_t, U]; L.HUF_optimalTableLog.argtypes = [U, C.c_size_t, U]
+    rng = np.random.default_rng(25)
+    for it in range(25):
+        n = int(rng.integers(300, 40000)); d = zoo(rng, n)
+        ca = (U * 256)(); cb = (U * 256)(); ma, mb = U(255), U(255)
+        ra = g_hist(ca, C.byref(ma), ptr(d), n); rb = lib.HIST_count(cb, C.byref(mb), ptr(d), n)
+        assert ra == rb and ma.value == mb.value and list(ca) == list(cb)
+        msv = ma.value
+        if ra == n or msv == 0:
+            continue
+        tl = lib.FSE_optimalTableLog(12, n, msv)
+        assert tl == L.FSE_optimalTableLog(12, n, msv)
+        na = (C.c_short * 256)(); nb_ = (C.c_short * 256)()
+        assert g_norm(na, tl, ca, n, msv) == lib.FSE_normalizeCount(nb_, tl, cb, n, msv)
+        assert list(na)[:msv + 1] == list(nb_)[:msv + 1]
+        ha = np.zeros(600, np.uint8); hb = np.zeros(600, np.uint8)
+        wa = g_wn(ptr(ha), 600, na, msv, tl); wb = lib.FSE_writeNCount(ptr(hb), 600, nb_, msv, tl)
+        assert wa == wb and bytes(ha[:wa]) == bytes(hb[:wb])
+        xa = (C.c_short * 256)(); xb = (C.c_short * 256)(); m1, m2, t1, t2 = U(255), U(255), U(0), U(0)
+        assert g_rn(xa, C.byref(m1), C.byref(t1), ptr(ha), wa) == lib.FSE_readNCount(xb, C.byref(m2), C.byref(t2), ptr(hb), wb)
+        assert (m1.value, t1.value) == (m2.value, t2.value) and list(xa)[:msv + 1] == list(xb)[:msv + 1]
+        cta = np.zeros(1 + 2048 + 512, np.uint32); ctb = np.zeros_like(cta)
+        assert g_ct(ptr(cta), na, msv, tl) == lib.FSE_buildCTable(ptr(ctb), nb_, msv, tl) == 0
+        half = 1 + (1 << (tl - 1))
+        assert np.array_equal(cta[:half], ctb[:half])
+        for s in range(msv + 1):
+            assert cta[half + 2 * s + 1] == ctb[half + 2 * s + 1]
+            if na[s] != 0:
+                assert cta[half + 2 * s] == ctb[half + 2 * s]
+        dta = np.zeros(1 + 4096, np.uint32); dtb = np.zeros_like(dta)
+        assert g_dt(ptr(dta), na, msv, tl) == lib.FSE_buildDTable(ptr(dtb), nb_, msv, tl) == 0
+        assert np.array_equal(dta[:1 + (1 << tl)], dtb[:1 + (1 << tl)])
+        # Huffman side
+        hl = lib.HUF_optimalTableLog(12, n, msv)
+        ta = np.zeros(256, np.uint32); tb = np.zeros(256, np.uint32)
+        r1 = g_hct(ptr(ta), ca, msv, hl); r2 = lib.HUF_buildCTable(ptr(tb), cb, msv, hl)
+        assert r1 == r2 and np.array_equal(ta[:msv + 1] & 0xFFFFFF, tb[:msv + 1] & 0xFFFFFF)
+        ha = np.zeros(300, np.uint8); hb = np.zeros(300, np.uint8)
+        wa = g_hw(ptr(ha), 300, ptr(ta), msv, r1); wb = lib.HUF_writeCTable(ptr(hb), 300, ptr(tb), msv, r2)
+        assert wa == wb
+        if is_error(wa):
+            continue
+        assert bytes(ha[:wa]) == bytes(hb[:wb])
+        wA = np.zeros(260, np.uint8); wB = np.zeros(260, np.uint8); rsA = (C.c_uint32 * 17)(); rsB = (C.c_uint32 * 17)()
+        nA, nB, tA, tB = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        sa = g_hrs(ptr(wA), 256, rsA, C.byref(nA), C.byref(tA), ptr(ha), wa)
+        sb = lib.HUF_readStats(ptr(wB), 256, rsB, C.byref(nB), C.byref(tB), ptr(hb), wb)
+        assert sa == sb
+        if is_error(sa):
+            continue
+        assert (nA.value, tA.value) == (nB.value, tB.value) and bytes(wA[:nA.value]) == bytes(wB[:nB.value]) and list(rsA)[:13] == list(rsB)[:13]
+        dA = np.zeros(1 + 2048, np.uint32); dB = np.zeros(1 + 2048, np.uint32); dA[0] = dB[0] = 11 * 0x01000001
+        assert g_hdt(ptr(dA), ptr(ha), wa) == lib.HUF_readDTableX1(ptr(dB), ptr(hb), wb) == wa
+        ncell = 1 + ((1 << tA.value) + 1) // 2
+        assert np.array_equal(dA[:ncell], dB[:ncell])
+
+
+@pytest.mark.parametrize("codec,p,mib", [("huf", 0.14, 64), ("fse", 0.80, 16)])
+def test_large_roundtrip_property(codec, p, mib):
+    """BASELINE sizes are too big for the CPU checker in a test: use encode -> decode == identity, a
+    checksum of per-block sizes against a CPU sample, and the GPU<->CPU cross-decode on that sample"""
+    n = mib << 20
+    data = probagen(n, p)
+    d = _dev(data)
+    cbuf, cs = ENC[codec](d, BLOCK, SLOT, 255, 12)
+    out, res = DEC[codec](cbuf, cs, n, BLOCK, SLOT, orig=d)
+    torch.cuda.synchronize()
+    assert torch.equal(out, d)
+    assert bool((res == BLOCK).all())
+    sample = slice(0, 64 * BLOCK)
+    wc, wcs, _ = cpu_compress(codec, data[sample], slot=SLOT)
+    assert np.array_equal(cs[:64].cpu().numpy().view(np.uint64), wcs)
+    got = cbuf[:64 * SLOT].cpu().numpy()
+    for b in range(64):
+        assert np.array_equal(got[b * SLOT: b * SLOT + int(wcs[b])], wc[b * SLOT: b * SLOT + int(wcs[b])])
