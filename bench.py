@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the judged benchmark: BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config[1] of BASELINE.json): probagen P=14%, 1 GiB per GPU, Huff0 4X encode + decode on
+32 KB blocks with the reference harness' parameters (maxSymbolValue 255, tableLog 12, slot =
+FSE_compressBound(32768) = 33,548 B; programs/bench.c:98,113,355,569).  One STEP = HUF_compress2 of
+every block of the batch followed by HUF_decompress of every block (one batched launch each).
+  value  = uncompressed bytes that went through encode+decode per second, whole job (all GPUs),
+           inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e    = the same metric through the host-buffer C-ABI calls (FSEB200_compress_host /
+           FSEB200_decompress_host): pinned host buffers, H2D/D2H copies inside the timed region.
+  roofline = dominant kernel's algorithmic bytes (S read + C written for encode, C read + S written
+           for decode) / its CUDA-event duration, against MEASURED_PEAKS.json.
+  cpu_baseline = the reference's own CPU path (oracle/_ref, compiled from the unmodified reference)
+           on this box's host cores, same workload, timed in the same run (rank 0, N=1).
+Multi-GPU: blocks are independent, so each rank owns a 1 GiB shard of the generator's stream
+(weak scaling, no data-path collective); NCCL is only used for the barrier / max-over-ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 32768
+SLOT = 512 + BLOCK + (BLOCK >> 7) + 4 + 8          # FSE_compressBound(32768), programs/bench.c:355
+METRIC = "encode+decode GB/s (uncompressed) per GPU on 32 KB blocks; bit-exact vs ref"
+CODEC_ID = {"fse": 0, "huf": 1, "u16": 2}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mib", type=int, default=1024, help="uncompressed MiB per GPU (BASELINE config: 1024)")
+    ap.add_argument("--codec", default="huf", choices=["huf", "fse"])
+    ap.add_argument("--p", type=float, default=0.14)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU checker access (bench.py is one of the few places allowed to execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def load_checker():
+    """(lib, kind): the compiled reference when its prebuilt .so travelled with the snapshot, else the port"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libfse_ref.so")
+    if os.path.exists(ref):
+        L = C.CDLL(ref)
+        L.refshim_compress_blocks.restype = C.c_double
+        L.refshim_compress_blocks.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint, C.c_int]
+        L.refshim_decompress_blocks.restype = C.c_double
+        L.refshim_decompress_blocks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        return L, "reference"
+    port = os.path.join(ROOT, "oracle", "_build", "libfse_oracle.so")
+    if not os.path.exists(port):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    L = C.CDLL(port)
+    L.orc_compress_blocks.restype = C.c_size_t
+    L.orc_compress_blocks.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint]
+    L.orc_decompress_blocks.restype = C.c_size_t
+    L.orc_decompress_blocks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    return L, "port"
+
+
+def cpu_roundtrip(L, kind, codec, data, cbuf, cs, out, res, threads):
+    """one compress + decompress pass of the CPU implementation over `data`; returns (t_comp, t_decomp) seconds"""
+    import numpy as np
+    cid = CODEC_ID[codec]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = len(data)
+    if kind == "reference":
+        tc = L.refshim_compress_blocks(cid, p(data), n, BLOCK, p(cbuf), SLOT, p(cs), 255, 12, threads)
+        td = L.refshim_decompress_blocks(cid, p(out), p(data), n, BLOCK, p(cbuf), SLOT, p(cs), p(res), threads)
+        return tc, td
+    nb = (n + BLOCK - 1) // BLOCK
+    per = (nb + threads - 1) // threads
+
+    def part(fn_c, t):
+        b0 = t * per; b1 = min(nb, b0 + per)
+        if b0 >= b1:
+            return
+        o = b0 * BLOCK; m = min(n, b1 * BLOCK) - o
+        if fn_c:
+            L.orc_compress_blocks(cid, data[o:].ctypes.data_as(C.c_void_p), m, BLOCK, cbuf[b0 * SLOT:].ctypes.data_as(C.c_void_p), SLOT,
+                                  cs[b0:].ctypes.data_as(C.c_void_p), 255, 12)
+        else:
+            L.orc_decompress_blocks(cid, out[o:].ctypes.data_as(C.c_void_p), data[o:].ctypes.data_as(C.c_void_p), m, BLOCK,
+                                    cbuf[b0 * SLOT:].ctypes.data_as(C.c_void_p), SLOT, cs[b0:].ctypes.data_as(C.c_void_p),
+                                    res[b0:].ctypes.data_as(C.c_void_p))
+    ts = []
+    for fn_c in (True, False):
+        th = [threading.Thread(target=part, args=(fn_c, t)) for t in range(threads)]
+        t0 = time.perf_counter(); [x.start() for x in th]; [x.join() for x in th]; ts.append(time.perf_counter() - t0)
+    return ts[0], ts[1]
+
+
+def cpu_probagen(n, p):
+    import numpy as np
+    port = os.path.join(ROOT, "oracle", "_build", "libfse_oracle.so")
+    if not os.path.exists(port):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    L = C.CDLL(port)
+    L.orc_probagen.restype = None
+    L.orc_probagen.argtypes = [C.c_void_p, C.c_size_t, C.c_double]
+    a = np.empty(n, np.uint8)
+    L.orc_probagen(a.ctypes.data_as(C.c_void_p), n, p)
+    return a
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []; self.stop = False; self.index = index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                            timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.t.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_note(kernel):
+    """dram bytes per launch from the committed ncu capture, if one exists for this kernel"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(kernel)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0                                                   # rank 0 alone times the CPU arm
+    import numpy as np
+    L, kind = load_checker()
+    threads = os.cpu_count() or 1
+    n = a.mib << 20
+    if threads < 16:
+        n = min(n, 256 << 20)                                     # bounded sample on small hosts
+    data = cpu_probagen(n, a.p)
+    nb = (n + BLOCK - 1) // BLOCK
+    cbuf = np.zeros(nb * SLOT + 64, np.uint8); cs = np.zeros(nb, np.uint64)
+    out = np.zeros(n, np.uint8); res = np.zeros(nb, np.uint64)
+    for _ in range(max(a.warmup, 1)):
+        cpu_roundtrip(L, kind, a.codec, data, cbuf, cs, out, res, threads)
+    assert np.array_equal(out, data)
+    tc = td = 0.0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        x, y = cpu_roundtrip(L, kind, a.codec, data, cbuf, cs, out, res, threads); tc += x; td += y
+    wall = time.perf_counter() - t0
+    val = n * a.steps / (tc + td) / 1e9
+    sample = "%d MiB of probagen P=%.0f%% (%d blocks), all %d host threads, %d steps" % (n >> 20, a.p * 100, nb, threads, a.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(1e3 * (tc + td) / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic (probagen restatement, seed 1)",
+            "config": {"workload": "probagen P=%.0f%% %d MiB, %s encode+decode, 32 KB blocks, (255,12)" % (a.p * 100, n >> 20, a.codec.upper()),
+                       "block_size": BLOCK, "slot": SLOT, "host_threads": threads},
+            "encode_gbs": round(n * a.steps / tc / 1e9, 3), "decode_gbs": round(n * a.steps / td / 1e9, 3),
+            "compressed_ratio": round(float(cs.astype(np.float64).sum()) / n, 5), "wall_s": round(wall, 2),
+            "cpu_baseline": {"value": round(val, 3), "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": round(val, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import finitestateentropy_b200 as fb
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = fb.lib()
+    for nm, args in (("FSEB200_probagen", [C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p]),
+                     ("FSEB200_compress_host", [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint]),
+                     ("FSEB200_decompress_host", [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p])):
+        f = getattr(L, nm); f.restype = C.c_size_t; f.argtypes = args
+    dev = torch.device("cuda", local)
+    n = a.mib << 20
+    nb = (n + BLOCK - 1) // BLOCK
+    src = torch.empty(n, dtype=torch.uint8, device=dev)
+    cbuf = torch.empty(nb * SLOT + 64, dtype=torch.uint8, device=dev)
+    cs = torch.empty(nb, dtype=torch.int64, device=dev)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    res = torch.empty(nb, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    assert L.FSEB200_probagen(src.data_ptr(), n, rank * n, a.p, stream) == 0     # this rank's shard of the generator stream
+    enc = fb.huf_compress_batch if a.codec == "huf" else fb.fse_compress_batch
+    dec = fb.huf_decompress_batch if a.codec == "huf" else fb.fse_decompress_batch
+
+    def step():
+        enc(src, BLOCK, SLOT, 255, 12, cbuf=cbuf, csizes=cs)
+        dec(cbuf, cs, n, BLOCK, SLOT, out=out, results=res, orig=src)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    # ---- parity gate of the run itself: round trip + byte identity against the CPU checker on a sample ----
+    ok_rt = bool(torch.equal(out, src)) and bool((res[:-1] == BLOCK).all())
+    csum = int(cs.sum().item())
+    bit_exact = None
+    if rank == 0:
+        try:
+            Lc, kind = load_checker()
+            k = min(nb, 256)
+            h = src[:k * BLOCK].cpu().numpy()
+            wc = np.zeros(k * SLOT + 64, np.uint8); wcs = np.zeros(k, np.uint64); wo = np.zeros(k * BLOCK, np.uint8); wr = np.zeros(k, np.uint64)
+            cpu_roundtrip(Lc, kind, a.codec, h, wc, wcs, wo, wr, min(os.cpu_count() or 1, 16))
+            g_cs = cs[:k].cpu().numpy().view(np.uint64); g_c = cbuf[:k * SLOT].cpu().numpy()
+            bit_exact = bool(np.array_equal(g_cs, wcs)) and all(
+                np.array_equal(g_c[b * SLOT: b * SLOT + int(wcs[b])], wc[b * SLOT: b * SLOT + int(wcs[b])]) for b in range(k))
+        except Exception as exc:                                   # checker unavailable: say so, do not guess
+            bit_exact = "unchecked: %r" % (exc,)
+    # ---- timed region: K steps, events on the launching (torch current) stream ----
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.__enter__()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(a.steps):
+        ev[i][0].record(); enc(src, BLOCK, SLOT, 255, 12, cbuf=cbuf, csizes=cs)
+        ev[i][1].record(); dec(cbuf, cs, n, BLOCK, SLOT, out=out, results=res, orig=src)
+        ev[i][2].record()
+    t1.record()
+    barrier()
+    if sampler:
+        sampler.__exit__()
+    total_ms = t0.elapsed_time(t1)
+    enc_ms = sum(ev[i][0].elapsed_time(ev[i][1]) for i in range(a.steps)) / a.steps
+    dec_ms = sum(ev[i][1].elapsed_time(ev[i][2]) for i in range(a.steps)) / a.steps
+    tm = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = [float(x) for x in tm.cpu()]
+    value = world * n * a.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside the timed region) ----
+    e2e = None
+    if not a.no_e2e:
+        h_src = torch.empty(n, dtype=torch.uint8, pin_memory=True); h_src.copy_(src)
+        h_c = torch.empty(nb * SLOT + 64, dtype=torch.uint8, pin_memory=True)
+        h_cs = torch.empty(nb, dtype=torch.int64, pin_memory=True)
+        h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        h_res = torch.empty(nb, dtype=torch.int64, pin_memory=True)
+        cid = CODEC_ID[a.codec]
+
+        def host_step():
+            r1 = L.FSEB200_compress_host(cid, h_c.data_ptr(), SLOT, h_cs.data_ptr(), h_src.data_ptr(), n, BLOCK, 255, 12)
+            r2 = L.FSEB200_decompress_host(cid, h_out.data_ptr(), n, BLOCK, h_c.data_ptr(), SLOT, h_cs.data_ptr(), h_res.data_ptr(), h_src.data_ptr())
+            assert r1 == 0 and r2 == 0
+        host_step()
+        ok_e2e = bool(torch.equal(h_out, h_src))
+        ke = max(1, min(a.steps, 3))
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(ke):
+            host_step()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = float(tw.cpu()[0])
+        e2e = {"value": round(world * n * ke / wall / 1e9, 3), "unit": "GB/s", "steps": ke, "roundtrip_ok": ok_e2e,
+               "h2d_bytes_per_step": n + nb * SLOT + 8 * nb, "d2h_bytes_per_step": nb * SLOT + 8 * nb + n + 8 * nb,
+               "api": "FSEB200_compress_host + FSEB200_decompress_host (pinned host buffers, 64 MiB chunks on 3 streams)"}
+        del h_src, h_c, h_out
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    # ---- roofline of the dominant kernel (algorithmic bytes: S + C each way) ----
+    peak, peak_src = measured_peak()
+    alg = n + csum
+    kern = {"huf_encode_kernel" if a.codec == "huf" else "fse_encode_kernel": enc_ms, "huf_decode_kernel" if a.codec == "huf" else "fse_decode_kernel": dec_ms}
+    dom = max(kern, key=kern.get)
+    roof = lambda ms: round(alg / (ms * 1e-3) / 1e9, 2)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": roof(kern[dom]), "peak": peak, "unit": "GB/s",
+                "frac": round(roof(kern[dom]) / peak, 4), "traffic": traffic_note(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg,
+                "all_kernels": {k: {"ms": round(v, 4), "achieved": roof(v), "frac": round(roof(v) / peak, 4)} for k, v in kern.items()}}
+    # ---- the reference's CPU path on this box's host cores, same run (N=1 only) ----
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        try:
+            Lc, kind = load_checker()
+            threads = os.cpu_count() or 1
+            m = n if threads >= 16 else min(n, 128 << 20)
+            h = src[:m].cpu().numpy(); k = (m + BLOCK - 1) // BLOCK
+            wc = np.zeros(k * SLOT + 64, np.uint8); wcs = np.zeros(k, np.uint64); wo = np.zeros(m, np.uint8); wr = np.zeros(k, np.uint64)
+            cpu_roundtrip(Lc, kind, a.codec, h, wc, wcs, wo, wr, threads)
+            reps = 3; tc = td = 0.0
+            for _ in range(reps):
+                x, y = cpu_roundtrip(Lc, kind, a.codec, h, wc, wcs, wo, wr, threads); tc += x; td += y
+            one = min(m, 64 << 20)
+            x1, y1 = cpu_roundtrip(Lc, kind, a.codec, h[:one], wc, wcs, wo, wr, 1)
+            cpu = {"value": round(m * reps / (tc + td) / 1e9, 3), "unit": "GB/s", "cores": threads, "kind": kind,
+                   "sample": "%d MiB of the same input, %d reps, encode %.2f GB/s + decode %.2f GB/s" % (m >> 20, reps, m * reps / tc / 1e9, m * reps / td / 1e9),
+                   "single_thread": {"value": round(one / (x1 + y1) / 1e9, 4), "encode_gbs": round(one / x1 / 1e9, 4), "decode_gbs": round(one / y1 / 1e9, 4),
+                                     "sample": "%d MiB" % (one >> 20)}}
+        except Exception as exc:
+            cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+    line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": round(total_ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic (probagen restatement generated in HBM, seed 1, shard = rank * size)",
+            "config": {"workload": "probagen P=%.0f%% %d MiB per GPU, %s encode+decode, 32 KB blocks, (255,12)" % (a.p * 100, a.mib, "Huff0 4X" if a.codec == "huf" else "FSE"),
+                       "block_size": BLOCK, "slot": SLOT, "blocks_per_gpu": nb, "l2": "inputs (%d MiB) larger than the 126 MB L2" % a.mib,
+                       "sharding": "independent blocks, contiguous shard per rank, no data-path collective"},
+            "encode_gbs_per_gpu": round(n / (enc_ms * 1e-3) / 1e9, 2), "decode_gbs_per_gpu": round(n / (dec_ms * 1e-3) / 1e9, 2),
+            "per_gpu": round(value / world, 3), "compressed_ratio": round(csum / n, 5),
+            "bit_exact": bit_exact, "roundtrip_ok": ok_rt,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * a.steps,
+            "clocks": sampler.summary() if sampler else None}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))

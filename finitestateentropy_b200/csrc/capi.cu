@@ -25,6 +25,8 @@ cudaError_t launch_fseu16_decode(const BatchGeom&, void*, const void*, const u64
 cudaError_t launch_fseu16_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
 cudaError_t launch_hist(const void*, u64, u32, u32*, u64*, cudaStream_t);
 cudaError_t launch_micro(int, const MicroArgs&, void*, u64*, cudaStream_t);
+cudaError_t launch_gen8(void*, u64, u64, const void*, u32, cudaStream_t);
+cudaError_t launch_gen16(void*, u64, u64, const void*, u32, cudaStream_t);
 }
 
 using namespace fseb;
@@ -416,4 +418,137 @@ FSEB_API size_t HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSi
     unsigned const tl = (hdr >> 16) & 0xFF;
     m.down(DTable, 16384, sizeof(unsigned) + ((size_t)1 << tl) * 2);
     return (size_t)r;
+}
+
+// ================================================================================================
+// measurement inputs (programs/probaGenerator.c:95-126, programs/fuzzerU16.c:107-134) generated in HBM
+// ================================================================================================
+FSEB_API size_t FSEB200_probagen(void* dDst, size_t nBytes, size_t streamOffset, double p, void* stream)
+{
+    unsigned char table[4096];
+    int remaining = 4096; unsigned pos = 0, sym = 0;
+    if (p == 0.0) p = 0.005;
+    while (remaining) {
+        unsigned n = (unsigned)(remaining * p);
+        if (!n) n = 1;
+        unsigned const end = pos + n;
+        while (pos < end) table[pos++] = (unsigned char)sym;
+        sym++; remaining -= (int)n;
+    }
+    void* dT = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMallocAsync(&dT, sizeof(table), st));
+    CK(cudaMemcpyAsync(dT, table, sizeof(table), cudaMemcpyHostToDevice, st));
+    cudaError_t const e = launch_gen8(dDst, nBytes, streamOffset, dT, 1u, st);
+    CK(cudaStreamSynchronize(st));                                     // `table` lives on this stack frame
+    CK(cudaFreeAsync(dT, st));
+    return ok_or_generic(e);
+}
+FSEB_API size_t FSEB200_genU16(void* dDst, size_t nSymbols, size_t streamOffset, unsigned start, double p, unsigned seed, void* stream)
+{
+    unsigned short table[4096];
+    unsigned remaining = 4096, pos = 0; unsigned short v = (unsigned short)start;
+    while (remaining) {
+        unsigned const n = (unsigned)(remaining * p) + 1;
+        unsigned const end = pos + n;
+        while (pos < end) table[pos++] = v;
+        v++; if (v >= U16_MAX_SV) v = 1;
+        remaining -= n;
+    }
+    void* dT = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMallocAsync(&dT, sizeof(table), st));
+    CK(cudaMemcpyAsync(dT, table, sizeof(table), cudaMemcpyHostToDevice, st));
+    cudaError_t const e = launch_gen16(dDst, nSymbols, streamOffset, dT, seed, st);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeAsync(dT, st));
+    return ok_or_generic(e);
+}
+
+// ================================================================================================
+// tier 1b: whole-batch calls on HOST buffers (what an unmodified host program would hand over):
+// the batch is cut into chunks that are copied in, processed and copied out on alternating streams so
+// that PCIe transfers overlap the kernels.  codec: 0 = FSE, 1 = HUF, 2 = FSE-U16.
+// ================================================================================================
+namespace {
+struct HostPipe {
+    enum { NS = 3 };
+    cudaStream_t st[NS] = { nullptr, nullptr, nullptr };
+    unsigned char* dA[NS] = { nullptr, nullptr, nullptr };   // uncompressed side
+    unsigned char* dB[NS] = { nullptr, nullptr, nullptr };   // compressed slots
+    u64* dS[NS] = { nullptr, nullptr, nullptr };             // sizes + results
+    size_t capA = 0, capB = 0, capS = 0;
+    std::mutex mu;
+    void ensure(size_t a, size_t b, size_t s)
+    {
+        for (int i = 0; i < NS; i++) if (!st[i]) CK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        if (a > capA) { for (int i = 0; i < NS; i++) { if (dA[i]) CK(cudaFree(dA[i])); CK(cudaMalloc(&dA[i], a + 256)); } capA = a; }
+        if (b > capB) { for (int i = 0; i < NS; i++) { if (dB[i]) CK(cudaFree(dB[i])); CK(cudaMalloc(&dB[i], b + 256)); } capB = b; }
+        if (s > capS) { for (int i = 0; i < NS; i++) { if (dS[i]) CK(cudaFree(dS[i])); CK(cudaMalloc(&dS[i], 2 * s * sizeof(u64))); } capS = s; }
+    }
+};
+HostPipe& pipe() { static HostPipe p; return p; }
+const size_t CHUNK_BLOCKS = 2048;                                     // 64 MiB of 32 KB blocks per chunk
+}
+
+FSEB_API size_t FSEB200_compress_host(int codec, void* hCBuf, size_t slot, size_t* hCSizes, const void* hSrc, size_t srcTotal,
+                                      size_t blockSize, unsigned maxSymbolValue, unsigned tableLog)
+{
+    if (blockSize == 0 || slot > 0xFFFFFFFFull || codec < 0 || codec > 2) return (size_t)err(E_SRC_WRONG);
+    enc_fn const fn = codec == 0 ? launch_fse_encode : codec == 1 ? launch_huf_encode : launch_fseu16_encode;
+    HostPipe& P = pipe();
+    std::lock_guard<std::mutex> lock(P.mu);
+    size_t const nb = (srcTotal + blockSize - 1) / blockSize;
+    P.ensure(CHUNK_BLOCKS * blockSize, CHUNK_BLOCKS * slot, CHUNK_BLOCKS);
+    int k = 0;
+    for (size_t b0 = 0; b0 < nb; b0 += CHUNK_BLOCKS, k = (k + 1) % HostPipe::NS) {
+        size_t const cb = nb - b0 < CHUNK_BLOCKS ? nb - b0 : CHUNK_BLOCKS;
+        size_t const off = b0 * blockSize;
+        size_t const bytes = (off + cb * blockSize <= srcTotal) ? cb * blockSize : srcTotal - off;
+        cudaStream_t s = P.st[k];
+        CK(cudaMemcpyAsync(P.dA[k], (const unsigned char*)hSrc + off, bytes, cudaMemcpyHostToDevice, s));
+        CK(fn(geom(bytes, blockSize, slot), P.dB[k], P.dS[k], P.dA[k], maxSymbolValue, tableLog, s));
+        CK(cudaMemcpyAsync((unsigned char*)hCBuf + b0 * slot, P.dB[k], cb * slot, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hCSizes + b0, P.dS[k], cb * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < HostPipe::NS; i++) CK(cudaStreamSynchronize(P.st[i]));
+    return 0;
+}
+
+FSEB_API size_t FSEB200_decompress_host(int codec, void* hDst, size_t dstTotal, size_t blockSize, const void* hCBuf, size_t slot,
+                                        const size_t* hCSizes, size_t* hResults, const void* hOrig)
+{
+    if (blockSize == 0 || slot > 0xFFFFFFFFull || codec < 0 || codec > 2) return (size_t)err(E_SRC_WRONG);
+    dec_fn const fn = codec == 0 ? launch_fse_decode : codec == 1 ? huf_dec_std : launch_fseu16_decode;
+    HostPipe& P = pipe();
+    std::lock_guard<std::mutex> lock(P.mu);
+    size_t const nb = (dstTotal + blockSize - 1) / blockSize;
+    P.ensure(CHUNK_BLOCKS * blockSize, CHUNK_BLOCKS * slot, CHUNK_BLOCKS);
+    int k = 0;
+    (void)hOrig;   // raw / RLE blocks: regenerated on the host below, exactly as bench.c:393-402 does
+    for (size_t b0 = 0; b0 < nb; b0 += CHUNK_BLOCKS, k = (k + 1) % HostPipe::NS) {
+        size_t const cb = nb - b0 < CHUNK_BLOCKS ? nb - b0 : CHUNK_BLOCKS;
+        size_t const off = b0 * blockSize;
+        size_t const bytes = (off + cb * blockSize <= dstTotal) ? cb * blockSize : dstTotal - off;
+        cudaStream_t s = P.st[k];
+        CK(cudaMemcpyAsync(P.dB[k], (const unsigned char*)hCBuf + b0 * slot, cb * slot, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(P.dS[k], hCSizes + b0, cb * sizeof(u64), cudaMemcpyHostToDevice, s));
+        CK(fn(geom(bytes, blockSize, slot), P.dA[k], P.dB[k], P.dS[k], P.dS[k] + CHUNK_BLOCKS, nullptr, s));
+        CK(cudaMemcpyAsync((unsigned char*)hDst + off, P.dA[k], bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hResults + b0, P.dS[k] + CHUNK_BLOCKS, cb * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < HostPipe::NS; i++) CK(cudaStreamSynchronize(P.st[i]));
+    if (hOrig) {
+        for (size_t b = 0; b < nb; b++) {
+            size_t const cs = hCSizes[b];
+            if (cs > 1 || (cs == 1 && codec == 2)) continue;
+            size_t const off = b * blockSize;
+            size_t const n = off + blockSize <= dstTotal ? blockSize : dstTotal - off;
+            if (cs == 0) std::memcpy((unsigned char*)hDst + off, (const unsigned char*)hOrig + off, n);
+            else if (codec != 1) std::memset((unsigned char*)hDst + off, ((const unsigned char*)hOrig)[off], n);
+            else continue;                                                  // HUF regenerates RLE blocks itself (lib/huf.h:62)
+            hResults[b] = n;
+        }
+    }
+    return 0;
 }

@@ -55,6 +55,21 @@ size_t FSEB200_FSEU16_compress_batch(void* dCBuf, size_t slot, size_t* dCSizes, 
 size_t FSEB200_FSEU16_decompress_batch(void* dDst, size_t dstTotal, size_t blockSize, const void* dCBuf, size_t slot,
                                        const size_t* dCSizes, size_t* dResults, const void* dOrig, void* stream);
 size_t FSEB200_batch_blocks(size_t total, size_t blockSize);
+
+/* Tier 1b -- the same batches on HOST buffers (pinned or pageable): chunks are copied in, processed and
+ * copied out on alternating CUDA streams so that PCIe transfers overlap the kernels.
+ * codec: 0 = FSE, 1 = HUF, 2 = FSE-U16.  Synchronous.  Raw / RLE blocks (cSize 0 / 1) are regenerated from
+ * hOrig on the host exactly as programs/bench.c:393-402 does. */
+size_t FSEB200_compress_host(int codec, void* hCBuf, size_t slot, size_t* hCSizes, const void* hSrc, size_t srcTotal,
+                             size_t blockSize, unsigned maxSymbolValue, unsigned tableLog);
+size_t FSEB200_decompress_host(int codec, void* hDst, size_t dstTotal, size_t blockSize, const void* hCBuf, size_t slot,
+                               const size_t* hCSizes, size_t* hResults, const void* hOrig);
+
+/* Measurement inputs generated directly in device memory: byte i of the output equals byte
+ * (streamOffset + i) of the reference generator's stream (programs/probaGenerator.c:95-126 with
+ * probability p, seed 1; programs/fuzzerU16.c:107-134 with the given start / p / seed). */
+size_t FSEB200_probagen(void* dDst, size_t nBytes, size_t streamOffset, double p, void* stream);
+size_t FSEB200_genU16(void* dDst, size_t nSymbols, size_t streamOffset, unsigned start, double p, unsigned seed, void* stream);
 int    FSEB200_device_count(void);
 
 /* ------------------------------------------------------------------------------------------------
