@@ -135,6 +135,77 @@ __device__ inline u64 cta_huf_build_ctable(u32* ctable, const u32* count, u32 ms
     return mb;
 }
 
+// Warp-cooperative variant (one warp builds one table; all operands in shared memory).
+// store: HNode[2*256+2]; lenOf: u8[256]; firstVal: u32[16].  Returns max code length or an error (warp-uniform).
+__device__ inline u64 warp_huf_build_ctable(u32* ctable, const u32* count, u32 msv, u32 maxBits,
+                                            HNode* store, u8* lenOf, u32* firstVal)
+{
+    unsigned const lane = threadIdx.x & 31u;
+    HNode* const nd = store + 1;
+    if (!maxBits) maxBits = HUF_DEF_TLOG;
+    if (msv > HUF_MAX_SV) return err(E_MSV_TOO_LARGE);
+    {   u64* const z = reinterpret_cast<u64*>(store);            // HNode is 8 bytes
+        for (u32 i = lane; i < 2 * 256 + 2; i += 32) z[i] = 0;
+    }
+    __syncwarp();
+    for (u32 s = lane; s <= msv; s += 32) {                      // rank by counting == stable sort by decreasing count
+        u32 const c = count[s];
+        u32 rank = 0;
+        for (u32 jj = 0; jj <= msv; jj++) { u32 const cj = count[jj]; rank += (cj > c) | ((cj == c) & (jj < s)); }
+        nd[rank].count = c; nd[rank].sym = (u8)s;
+    }
+    __syncwarp();
+    u32 mb = 0; int last = 0;
+    if (lane == 0) {
+        last = (int)msv; while (nd[last].count == 0) last--;
+        int fresh = 256, leaf = last, root = fresh + leaf - 1, inner = fresh;
+        nd[fresh].count = nd[leaf].count + nd[leaf - 1].count;
+        nd[leaf].parent = nd[leaf - 1].parent = (u16)fresh;
+        fresh++; leaf -= 2;
+        for (int n = fresh; n <= root; n++) nd[n].count = 1u << 30;
+        nd[-1].count = 1u << 31;
+        while (fresh <= root) {
+            int const a = (nd[leaf].count < nd[inner].count) ? leaf-- : inner++;
+            int const b = (nd[leaf].count < nd[inner].count) ? leaf-- : inner++;
+            nd[fresh].count = nd[a].count + nd[b].count;
+            nd[a].parent = nd[b].parent = (u16)fresh;
+            fresh++;
+        }
+        nd[root].len = 0;
+        for (int n = root - 1; n >= 256; n--) nd[n].len = (u8)(nd[nd[n].parent].len + 1);
+    }
+    last = __shfl_sync(0xFFFFFFFFu, last, 0);
+    __syncwarp();
+    for (int n = (int)lane; n <= last; n += 32) nd[n].len = (u8)(nd[nd[n].parent].len + 1);
+    __syncwarp();
+    if (lane == 0) {
+        mb = d_huf_limit_depth(nd, (u32)last, maxBits);
+        if (mb <= HUF_MAX_TLOG) {
+            u32 perLen[HUF_MAX_TLOG + 1];
+            for (u32 i = 0; i <= HUF_MAX_TLOG; i++) perLen[i] = 0;
+            for (int n = 0; n <= last; n++) perLen[nd[n].len]++;
+            u32 v = 0;
+            for (u32 i = 0; i <= HUF_MAX_TLOG; i++) firstVal[i] = 0;
+            for (int n = (int)mb; n > 0; n--) { firstVal[n] = v; v = (v + perLen[n]) >> 1; }
+        }
+    }
+    mb = __shfl_sync(0xFFFFFFFFu, mb, 0);
+    if (mb > HUF_MAX_TLOG) return err(E_GENERIC);
+    __syncwarp();
+    for (u32 s = lane; s <= msv; s += 32) lenOf[nd[s].sym] = nd[s].len;
+    __syncwarp();
+    for (u32 s = lane; s < 256; s += 32) {
+        if (s <= msv) {
+            u32 const len = lenOf[s];
+            u32 before = 0;
+            for (u32 jj = 0; jj < s; jj++) before += (lenOf[jj] == len);
+            ctable[s] = ((firstVal[len] + before) & 0xFFFF) | (len << 16);
+        } else ctable[s] = 0;
+    }
+    __syncwarp();
+    return mb;
+}
+
 // HUF_compressWeights, one lane.  wksp: >= 160 u32 of scratch.
 __device__ inline u64 d_huf_compress_weights(u8* out, u64 cap, const u8* w, u64 n, u32* wksp)
 {

@@ -9,60 +9,69 @@
 // speed heuristic only (lib/huf_decompress.c:1029-1051) and both regenerate identical bytes.
 //
 // B200 mapping ("lane per stream, table per bank"):
-//   * one CTA = 64 consecutive blocks = 256 streams = 256 threads; a warp holds the SAME stream
+//   * one CTA = up to 64 consecutive blocks = 256 streams = 256 threads; a warp holds the SAME stream
 //     index of 32 DIFFERENT blocks, so the 32 lanes of a table look-up hit 32 different tables;
-//   * the per-block decode table is a 9-bit first-level table of {nbBits, symbol} cells, interleaved
-//     as u16 main[512][64]: the cell of block j sits in column j, i.e. the 32 lanes of a warp
-//     (blocks 2*lane + parity) read 32 different banks -> conflict-free LDS for a random index;
-//   * codes longer than 9 bits (rare: their probability is < 2^-9 each) take a canonical-code
-//     fallback from <= 3 rank thresholds and the per-block list of symbols sorted by code length;
-//   * each lane keeps a 64-bit left-aligned bit window in two registers, refilled 32 bits at a time
-//     from a private 8-word shared-memory ring that the lane itself stages with aligned 16-byte
-//     global loads (one load in flight ahead of use), walking its stream backwards;
-//   * output: each lane packs 4 symbols per 32-bit store into its own quarter of the block.
+//   * per-block decode tables are interleaved by column: u16 main[512][64] is indexed by the top 9
+//     bits of the bit window, u16 sub[256][64] by the top tableLog bits for the few windows that start
+//     a code longer than 9 bits (Huff0 numbers the longest codes from 0, so those windows are exactly
+//     the values below a per-block threshold T).  Column j of a row sits in bank j/2, and a warp holds
+//     the even (or the odd) columns, so every look-up is bank-conflict free whatever the 32 indices;
+//   * the choice main/sub is a select, not a branch: the hot loop has no divergent control flow;
+//   * each lane keeps a 64-bit left-aligned bit window in two registers; every two symbols a
+//     predicated block merges the next 32-bit word, taken from a private 8-word shared-memory ring the
+//     lane stages itself with aligned 16-byte global loads issued one iteration ahead of use;
+//   * output: 8 symbols are packed into one 8-byte store per lane into its quarter of the block;
+//   * blocks whose long-code region exceeds 256 windows ("hard", e.g. near-flat 256-symbol alphabets),
+//     unaligned segments and ragged tails take a slower per-symbol loop with a canonical-code search;
+//   * the grid is shaped so that every SM gets the same number of blocks per round (a round = 2 CTAs
+//     per SM): blocksPerCta is chosen <= 64 from the batch size, see launch_huf_decode().
 #include "common.cuh"
 #include "huf_dev.cuh"
 
 namespace fseb {
 namespace hufd {
 
-constexpr int G = 64;             // blocks per CTA
+constexpr int G = 64;             // block columns per CTA
 constexpr int THREADS = 4 * G;    // one lane per stream
 constexpr int MAIN_BITS = 9;
 constexpr int MAIN_ROWS = 1 << MAIN_BITS;
+constexpr int SUB_ROWS = 256;
 constexpr int RING = 8;           // 32-bit words of stream look-ahead per lane
 constexpr u32 NOERR = 0xFFFFFFFFu;
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct __align__(16) Smem {
     u16 main[MAIN_ROWS][G];       // 64 KB   first-level table, column = block
-    u32 ring[RING][THREADS];      //  8 KB   per-lane stream words (column = thread)
-    u8  sorted[G][256];           // 16 KB   symbols ordered by (weight asc, symbol asc) == code order
+    u16 sub[SUB_ROWS][G];         // 32 KB   long-code windows (index < T); hard blocks park their sorted symbol list here
+    u32 ring[RING][THREADS];      //  8 KB   per-lane stream words (column = thread); table-build scratch before the streams start
     u16 rankEnd[HUF_MAX_TLOG + 2][G];   // end (exclusive) of weight w's range in tableLog-bit index space
-    u16 listStart[HUF_MAX_TLOG + 2][G]; // first position of weight w in sorted[]
+    u16 listStart[HUF_MAX_TLOG + 2][G]; // first position of weight w in the sorted symbol list
+    u16 longT[G];                 // number of tableLog-bit windows that start a code longer than 9 bits
     u8  tlog[G];
     u8  kind[G];                  // 0 = Huffman, 1 = raw copy, 2 = RLE, 3 = done/skip
+    u8  hard[G];
     u32 status[G];                // NOERR or (stage<<8 | error code), smallest wins
     u32 hsize[G];                 // header bytes
-    u8  weights[THREADS / 32][256];
     u32 rankStats[THREADS / 32][HUF_MAX_TLOG + 1];
     u16 rankRun[THREADS / 32][HUF_MAX_TLOG + 2];
 };
 
-// canonical-code look-up in tableLog-bit index space -> (nbBits | symbol << 8)
-__device__ __forceinline__ u32 canon_lookup(const Smem& sm, int blk, u32 idx, u32 tl, u32 wStart)
+// canonical-code look-up in tableLog-bit index space -> (nbBits | symbol << 8); `list(k)` yields the k-th symbol in code order
+template <typename ListFn>
+__device__ __forceinline__ u32 canon_lookup(const Smem& sm, int blk, u32 idx, u32 tl, u32& w, ListFn list)
 {
-    u32 w = wStart;
     while (idx >= sm.rankEnd[w][blk]) w++;
     u32 const first = (w == 1) ? 0u : sm.rankEnd[w - 1][blk];
     u32 const k = sm.listStart[w][blk] + ((idx - first) >> (w - 1));
-    return (tl + 1 - w) | ((u32)sm.sorted[blk][k] << 8);
+    return (tl + 1 - w) | (list(k) << 8);
 }
 
-// Builds the tables of block `blk` (group-local index) with one warp.
+// Builds the tables of block column `blk` with one warp.
 __device__ void setup_block(Smem& sm, int blk, const u8* csrc, u64 csize, int warp)
 {
     unsigned const lane = lane_id();
-    u8* const weights = sm.weights[warp];
+    u8* const weights = reinterpret_cast<u8*>(&sm.ring[0][0]) + warp * 512;   // per-warp scratch inside the (not yet used) ring
+    u8* const sorted = weights + 256;                                          // symbols ordered by (weight asc, symbol asc) == code order
     u32 nbSym = 0, tl = 0; u64 h = 0;
     if (lane == 0) {
         h = d_huf_read_stats(weights, 256, sm.rankStats[warp], &nbSym, &tl, csrc, csize);
@@ -78,63 +87,70 @@ __device__ void setup_block(Smem& sm, int blk, const u8* csrc, u64 csize, int wa
                 acc += sm.rankStats[warp][w] << (w - 1);
                 sm.rankEnd[w][blk] = (u16)(acc > 0xFFFF ? 0xFFFF : acc);
             }
-            sm.rankEnd[tl][blk] = (u16)((1u << tl) > 0xFFFF ? 0xFFFF : (1u << tl));
+            sm.rankEnd[tl][blk] = (u16)(1u << tl);
             sm.rankEnd[tl + 1][blk] = 0xFFFF;
+            u32 const T = (tl > MAIN_BITS) ? sm.rankEnd[tl - MAIN_BITS][blk] : 0u;     // weights 1..tl-9 <=> code length > 9
+            sm.longT[blk] = (u16)T;
+            sm.hard[blk] = (u8)(T > SUB_ROWS);
             sm.tlog[blk] = (u8)tl;
             sm.hsize[blk] = (u32)h;
         } else {
             atomicMin(&sm.status[blk], (u32)(0u << 8 | (u32)(0 - h)));
         }
     }
-    h = __shfl_sync(0xFFFFFFFFu, h, 0);
+    h = __shfl_sync(FULL, h, 0);
     if (is_err(h)) return;
-    nbSym = __shfl_sync(0xFFFFFFFFu, nbSym, 0);
-    tl = __shfl_sync(0xFFFFFFFFu, tl, 0);
+    nbSym = __shfl_sync(FULL, nbSym, 0);
+    tl = __shfl_sync(FULL, tl, 0);
     __syncwarp();
     // sorted symbol list: stable by weight, then symbol order (huf_decompress.c:158-183 fills cells in that order)
     for (u32 base = 0; base < nbSym; base += 32) {
         u32 const s = base + lane;
         u32 const w = (s < nbSym) ? weights[s] : 0u;
-        u32 const peers = __match_any_sync(0xFFFFFFFFu, w);
-        if (w) {
-            u32 const before = __popc(peers & ((1u << lane) - 1));
-            u32 const slot = sm.rankRun[warp][w] + before;
-            sm.sorted[blk][slot] = (u8)s;
-        }
+        u32 const peers = __match_any_sync(FULL, w);
+        if (w) sorted[sm.rankRun[warp][w] + __popc(peers & ((1u << lane) - 1))] = (u8)s;
         __syncwarp();
         if (w && (peers >> lane) == 1u) sm.rankRun[warp][w] = (u16)(sm.rankRun[warp][w] + __popc(peers));   // highest lane of the group
         __syncwarp();
     }
-    // first-level table: cell = nbBits | symbol<<8 ; nbBits == 0 marks "longer than 9 bits"
+    auto list = [&](u32 k) -> u32 { return sorted[k]; };
+    // first-level table: cell = nbBits | symbol<<8 (cells that start a longer code are never read: the select picks `sub`)
     {   u32 w = 1;
         for (u32 i = 0; i < MAIN_ROWS / 32; i++) {
             u32 const idx9 = lane * (MAIN_ROWS / 32) + i;
             u32 const idx = (tl >= MAIN_BITS) ? (idx9 << (tl - MAIN_BITS)) : (idx9 >> (MAIN_BITS - tl));
-            while (idx >= sm.rankEnd[w][blk]) w++;
-            u32 const first = (w == 1) ? 0u : sm.rankEnd[w - 1][blk];
-            u32 const k = sm.listStart[w][blk] + ((idx - first) >> (w - 1));
-            u32 const nb = tl + 1 - w;
-            sm.main[idx9][blk] = (u16)(nb <= MAIN_BITS ? (nb | ((u32)sm.sorted[blk][k] << 8)) : 0u);
+            u32 const e = canon_lookup(sm, blk, idx, tl, w, list);
+            sm.main[idx9][blk] = (u16)((e & 0xFF) <= MAIN_BITS ? e : 0u);
         }
     }
+    u32 const T = sm.longT[blk];
+    if (T <= SUB_ROWS) {
+        for (u32 idx = lane; idx < T; idx += 32) { u32 w = 1; sm.sub[idx][blk] = (u16)canon_lookup(sm, blk, idx, tl, w, list); }
+    } else {
+        for (u32 k = lane; k < 256; k += 32) sm.sub[k][blk] = sorted[k];        // hard block: keep the code-ordered symbol list
+    }
+    __syncwarp();
 }
+
+__device__ __forceinline__ u32 lds_u16(u32 addr) { u16 v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
 
 __global__ void __launch_bounds__(THREADS, 2)
 huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf, const u64* __restrict__ csizes,
-                  u64* __restrict__ results, const u8* __restrict__ orig, u32 flags)
+                  u64* __restrict__ results, const u8* __restrict__ orig, u32 flags, u32 gEff)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    u32 const blk0 = blockIdx.x * G;
+    u32 const blk0 = blockIdx.x * gEff;
+    u32 const blkEnd = min(blk0 + gEff, g.nBlocks);                         // this CTA owns blocks [blk0, blkEnd)
 
-    if (tid < G) { sm.status[tid] = NOERR; sm.kind[tid] = 3; sm.hsize[tid] = 0; sm.tlog[tid] = 0; }
+    if (tid < G) { sm.status[tid] = NOERR; sm.kind[tid] = 3; sm.hsize[tid] = 0; sm.tlog[tid] = 0; sm.longT[tid] = 0; sm.hard[tid] = 0; }
     __syncthreads();
 
-    // ---- classify blocks and build tables: warp w handles blocks w, w+8, ... of the group ----
+    // ---- classify blocks and build tables: warp w handles columns w, w+8, ... ----
     for (int j = warp; j < G; j += THREADS / 32) {
         u32 const b = blk0 + j;
-        if (b >= g.nBlocks) continue;                                   // warp-uniform
+        if (b >= blkEnd) continue;                                      // warp-uniform
         u64 const n = block_len(g, b);
         u64 const cs = csizes[b];
         int kind;
@@ -152,10 +168,10 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     __syncthreads();
 
     // ---- per-lane stream set-up: thread -> (block column, stream) ----
-    int const col = 2 * lane + (warp >> 2);          // block within group; a warp sees 32 distinct banks of main[][]
+    int const col = 2 * lane + (warp >> 2);          // a warp sees the 32 even (or odd) columns = 32 distinct banks
     int const strm = warp & 3;
     u32 const b = blk0 + col;
-    bool const live = (b < g.nBlocks) && sm.kind[col] == 0 && sm.status[col] == NOERR;
+    bool const live = (b < blkEnd) && sm.kind[col] == 0 && sm.status[col] == NOERR;
     u32 const n = live ? block_len(g, b) : 0;
     u32 const seg = (n + 3) / 4;
     u32 segLen = 0;                                  // symbols this lane must produce
@@ -165,25 +181,23 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     uint4 pend = make_uint4(0, 0, 0, 0);
     u32 const tl = sm.tlog[col];
 
-    auto load_chunk = [&](u32 qq) -> uint4 {         // aligned 16 bytes ending at chunkTop - 16*qq ; bytes below the stream start read as 0
+    auto chunk_addr = [&](u32 qq) -> u64 {           // aligned 16 bytes of chunk qq, clamped into the stream's own chunks (always readable)
+        u64 const lowest = sBegin & ~15ull;
+        u64 const a = chunkTop - 16ull * (qq + 1);
+        return (a < lowest || a >= chunkTop) ? lowest : a;
+    };
+    auto stage = [&](uint4 v, u32 qq) {              // chunk qq holds words 4qq..4qq+3 in descending address order; bytes below the stream read as 0
         u64 const top = chunkTop - 16ull * qq;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (top > sBegin && 16ull * qq < chunkTop) {
-            u64 const a = top - 16;
-            v = __ldg(reinterpret_cast<const uint4*>(a));
-            if (a < sBegin) {                        // zero the bytes that precede the stream
-                u32 const z = (u32)(sBegin - a);     // 1..15
-                u32* p = reinterpret_cast<u32*>(&v);
-                #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    int const zb = (int)z - 4 * i;
-                    if (zb >= 4) p[i] = 0; else if (zb > 0) p[i] &= 0xFFFFFFFFu << (8 * zb);
-                }
+        if (top <= sBegin || 16ull * qq >= chunkTop) v = make_uint4(0, 0, 0, 0);
+        else if (top - 16 < sBegin) {
+            u32 const z = (u32)(sBegin - (top - 16));            // 1..15 leading bytes to clear
+            u32* p = reinterpret_cast<u32*>(&v);
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int const zb = (int)z - 4 * i;
+                if (zb >= 4) p[i] = 0; else if (zb > 0) p[i] &= 0xFFFFFFFFu << (8 * zb);
             }
         }
-        return v;
-    };
-    auto stage = [&](uint4 v, u32 qq) {              // chunk qq holds words 4qq..4qq+3 in descending address order
         u32 const s0 = (4 * qq) & (RING - 1);
         sm.ring[s0 + 0][tid] = v.w; sm.ring[s0 + 1][tid] = v.z; sm.ring[s0 + 2][tid] = v.y; sm.ring[s0 + 3][tid] = v.x;
     };
@@ -211,84 +225,127 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
                         sBegin = (u64)(pay + off);
                         u64 const e = sBegin + len;                                  // one past the last byte
                         chunkTop = ((e - 1) & ~15ull) + 16;
-                        u32 const c0 = (u32)(8 * (chunkTop - e)) + (8 - hibit(last));   // garbage above the stream + zero padding + end mark
                         segLen = (strm < 3) ? seg : n - 3 * seg;
-                        stage(load_chunk(0), 0); stage(load_chunk(1), 1);
-                        q = 2; pend = load_chunk(2);
-                        k = c0 >> 5; r = c0 & 31;
-                        u32 const w0 = sm.ring[k & (RING - 1)][tid], w1 = sm.ring[(k + 1) & (RING - 1)][tid];
-                        nw = sm.ring[(k + 2) & (RING - 1)][tid];
-                        hi = __funnelshift_l(w1, w0, r); lo = w1 << r;
                     }
                 }
             }
         }
         if (code) atomicMin(&sm.status[col], (u32)((1u + strm) << 8 | code));
     }
-    __syncthreads();                                  // init verdicts of all four streams are in
+    __syncthreads();                                  // init verdicts of all four streams are in; table-build scratch (ring) is free now
     bool const go = live && sm.status[col] == NOERR;
     if (!go) segLen = 0;
+    // window initialisation (needs the ring, hence after the barrier)
+    if (go) {
+        const u8* const cs0 = cbuf + (u64)b * g.slot;
+        u64 const cs = csizes[b];
+        const u8* const pay = cs0 + sm.hsize[col];
+        u64 const psize = cs - sm.hsize[col];
+        u32 const l1 = rd16(pay), l2 = rd16(pay + 2), l3 = rd16(pay + 4);
+        u32 const l4 = (u32)(psize - 6 - l1 - l2 - l3);
+        u32 const off = 6 + (strm > 0 ? l1 : 0) + (strm > 1 ? l2 : 0) + (strm > 2 ? l3 : 0);
+        u32 const len = strm == 0 ? l1 : strm == 1 ? l2 : strm == 2 ? l3 : l4;
+        u8 const last = pay[off + len - 1];
+        u64 const e = sBegin + len;
+        u32 const c0 = (u32)(8 * (chunkTop - e)) + (8 - hibit(last));      // garbage above the stream + zero padding + end mark
+        stage(__ldg(reinterpret_cast<const uint4*>(chunk_addr(0))), 0);
+        stage(__ldg(reinterpret_cast<const uint4*>(chunk_addr(1))), 1);
+        q = 2; pend = __ldg(reinterpret_cast<const uint4*>(chunk_addr(2)));
+        k = c0 >> 5; r = c0 & 31;
+        u32 const w0 = sm.ring[k & (RING - 1)][tid], w1 = sm.ring[(k + 1) & (RING - 1)][tid];
+        nw = sm.ring[(k + 2) & (RING - 1)][tid];
+        hi = __funnelshift_l(w1, w0, r); lo = w1 << r;
+    }
 
     // ---- decode ----
-    const u16* const tab = &sm.main[0][col];
-    u32 const wLong = 1;                              // long codes start at weight 1
-    u32 const longShift = 32 - tl;
-    auto refill = [&]() {                             // a 32-bit boundary was crossed: merge the prefetched word
-        r &= 31; k++;
-        hi |= __funnelshift_l(nw, 0, r); lo = nw << r;
-        nw = sm.ring[(k + 2) & (RING - 1)][tid];
-    };
-    auto decode1 = [&]() -> u32 {                     // returns nbBits | symbol << 8 and advances the window
-        u32 e = tab[(hi >> (32 - MAIN_BITS)) * G];
-        if (__builtin_expect((e & 0xFF) == 0, 0)) e = canon_lookup(sm, col, hi >> longShift, tl, wLong);
-        hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0, lo, e);
-        r += e & 0xFF;
-        return e;
-    };
+    u32 const sMain = (u32)__cvta_generic_to_shared(&sm.main[0][col]);     // + row * 128
+    u32 const sSub = (u32)__cvta_generic_to_shared(&sm.sub[0][col]);
+    u32 const ringLo = (u32)__cvta_generic_to_shared(&sm.ring[0][tid]);
+    u32 const ringEnd = ringLo + RING * THREADS * 4;
+    u32 rp = ringLo + ((k + 2) & (RING - 1)) * (THREADS * 4);              // slot `nw` was read from; a refill advances it first
+    u32 const T = sm.longT[col];
+    u32 const shTl = 32 - (tl ? tl : 1);
+    bool const hardBlk = sm.hard[col] != 0;
+
     auto top_up = [&]() {                             // keep the ring ahead of the consumer (at most one chunk per 8 symbols)
-        if (4 * q <= k + 7) { stage(pend, q); q++; pend = load_chunk(q); }
+        if (4 * q <= k + 7) {
+            stage(pend, q); q++;
+            pend = __ldg(reinterpret_cast<const uint4*>(chunk_addr(q)));    // consumed no earlier than the next call
+        }
     };
+    // one symbol, branch-free: E = nbBits | symbol << 8, window advanced
+#define HUFD_LOOKUP(E) do { \
+        u32 const i12_ = hi >> shTl; \
+        u32 const aM_ = ((hi >> (32 - MAIN_BITS)) << 7) + sMain; \
+        u32 const aS_ = (i12_ << 7) + sSub; \
+        E = lds_u16(i12_ < T ? aS_ : aM_); \
+        hi = __funnelshift_l(lo, hi, E); lo = __funnelshift_l(0, lo, E); \
+    } while (0)
+    // merge the next word when the pair crossed a 32-bit boundary (bit 5 of the running count); all predicated
+#define HUFD_REFILL() asm volatile("{\n\t" \
+        ".reg .pred p, qq;\n\t.reg .b32 t;\n\t" \
+        "and.b32 t, %4, 32;\n\t" \
+        "setp.ne.u32 p, t, 0;\n\t" \
+        "and.b32 %4, %4, 31;\n\t" \
+        "shf.l.wrap.b32 t, %2, 0, %4;\n\t" \
+        "@p or.b32 %0, %0, t;\n\t" \
+        "@p shl.b32 %1, %2, %4;\n\t" \
+        "@p add.u32 %5, %5, 1;\n\t" \
+        "@p add.u32 %3, %3, %6;\n\t" \
+        "setp.ge.and.u32 qq, %3, %7, p;\n\t" \
+        "@qq sub.u32 %3, %3, %8;\n\t" \
+        "@p ld.shared.u32 %2, [%3];\n\t" \
+        "}" : "+r"(hi), "+r"(lo), "+r"(nw), "+r"(rp), "+r"(r), "+r"(k) : "n"(THREADS * 4), "r"(ringEnd), "n"(RING * THREADS * 4) : "memory")
 
     u32 pos = 0;
-    bool const aligned = ((reinterpret_cast<u64>(outp) & 7) == 0);   // 8-byte stores
-    if (aligned) {
+    bool const fastOk = go && !hardBlk && ((reinterpret_cast<u64>(outp) & 7) == 0);
+    if (fastOk) {
         u32 const nIter = segLen >> 3;
         for (u32 it = 0; it < nIter; it++) {
             top_up();
-            u32 o0 = 0, o1 = 0, e;
-            e = decode1(); o0 = __byte_perm(o0, e, 0x3215);
-            e = decode1(); o0 = __byte_perm(o0, e, 0x3250);
-            if (r >= 32) refill();
-            e = decode1(); o0 = __byte_perm(o0, e, 0x3510);
-            e = decode1(); o0 = __byte_perm(o0, e, 0x5210);
-            if (r >= 32) refill();
-            e = decode1(); o1 = __byte_perm(o1, e, 0x3215);
-            e = decode1(); o1 = __byte_perm(o1, e, 0x3250);
-            if (r >= 32) refill();
-            e = decode1(); o1 = __byte_perm(o1, e, 0x3510);
-            e = decode1(); o1 = __byte_perm(o1, e, 0x5210);
-            if (r >= 32) refill();
+            u32 o0, o1, e0, e1;
+            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
+            o0 = __byte_perm(e0, e1, 0x0051);                       // {sym0, sym1, x, x}
+            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
+            o0 = __byte_perm(o0, __byte_perm(e0, e1, 0x0051), 0x5410);
+            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
+            o1 = __byte_perm(e0, e1, 0x0051);
+            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
+            o1 = __byte_perm(o1, __byte_perm(e0, e1, 0x0051), 0x5410);
             *reinterpret_cast<uint2*>(outp + pos) = make_uint2(o0, o1);
             pos += 8;
         }
     }
-    while (pos < segLen) {                            // ragged tails and unaligned segments: one symbol at a time
-        if ((pos & 7) == 0) top_up();
-        u32 const e = decode1();
-        if (r >= 32) refill();
-        outp[pos++] = (u8)(e >> 8);
+    // ragged tails, unaligned segments and hard blocks: one symbol at a time
+    {
+        auto parked = [&](u32 kk) -> u32 { return sm.sub[kk][col] & 0xFFu; };
+        while (pos < segLen) {
+            if ((pos & 7) == 0) top_up();
+            u32 e;
+            u32 const idx = hi >> shTl;
+            if (idx < T) {
+                if (hardBlk) { u32 w = 1; e = canon_lookup(sm, col, idx, tl, w, parked); }
+                else e = sm.sub[idx][col];
+            } else e = sm.main[hi >> (32 - MAIN_BITS)][col];
+            hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0, lo, e);
+            r += e & 0xFF;
+            HUFD_REFILL();
+            outp[pos++] = (u8)(e >> 8);
+        }
     }
+#undef HUFD_LOOKUP
+#undef HUFD_REFILL
 
     // ---- verdict: every stream must be consumed exactly (huf_decompress.c:348-349) ----
     if (go) {
-        u64 const consumed = 32ull * k + r;
+        u64 const consumed = 32ull * k + (r & 31);
         u64 const expect = 8ull * (chunkTop - sBegin);
         if (consumed != expect) atomicMin(&sm.status[col], (u32)(5u << 8 | E_CORRUPT));
     }
     __syncthreads();
     if (tid < G) {
         u32 const bb = blk0 + tid;
-        if (bb < g.nBlocks && sm.kind[tid] == 0) {
+        if (bb < blkEnd && sm.kind[tid] == 0) {
             u32 const st = sm.status[tid];
             results[bb] = (st == NOERR) ? (u64)block_len(g, bb) : err(st & 0xFF);
         }
@@ -316,15 +373,25 @@ cudaError_t launch_huf_decode(const BatchGeom& g, void* dst, const void* cbuf, c
                               const void* orig, cudaStream_t stream, u32 flags)
 {
     static bool configured = false;
+    static int numSMs = 148;
     size_t const smem = sizeof(hufd::Smem);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(hufd::huf_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
     if (g.nBlocks == 0) return cudaSuccess;
-    unsigned const grid = (g.nBlocks + hufd::G - 1) / hufd::G;
-    hufd::huf_decode_kernel<<<grid, hufd::THREADS, smem, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig, flags);
+    // balanced rounds: every lane decodes a whole stream, so a CTA's run time does not depend on how many
+    // blocks it holds; give each SM the same number of blocks per round (2 CTAs resident per SM).
+    u32 const slots = 2u * (u32)numSMs;
+    u32 const rounds = (g.nBlocks + slots * hufd::G - 1) / (slots * hufd::G);
+    u32 gEff = (g.nBlocks + slots * rounds - 1) / (slots * rounds);
+    if (gEff > (u32)hufd::G) gEff = hufd::G;
+    if (gEff < 1) gEff = 1;
+    unsigned const grid = (g.nBlocks + gEff - 1) / gEff;
+    hufd::huf_decode_kernel<<<grid, hufd::THREADS, smem, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig, flags, gEff);
     return cudaGetLastError();
 }
 

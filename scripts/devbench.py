@@ -1,34 +1,42 @@
 """Developer micro-benchmark (not the judged bench.py): times one batched kernel on HBM-resident data.
-usage: python scripts/devbench.py huf_dec [MiB] [p]"""
-import os, sys, time
+usage: python scripts/devbench.py {huf_enc|huf_dec|fse_enc|fse_dec|u16_enc|u16_dec} [MiB] [p] [iters]"""
+import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-import numpy as np, torch
-from helpers import probagen
-from gpu_common import cpu_compress, BLOCK, SLOT
+import torch
 import finitestateentropy_b200 as fb
 
 what = sys.argv[1] if len(sys.argv) > 1 else "huf_dec"
 mib = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 p = float(sys.argv[3]) if len(sys.argv) > 3 else 0.14
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 n = mib << 20
-t0 = time.time(); data = probagen(n, p); t1 = time.time()
-codec = "huf" if what.startswith("huf") else "fse"
-cbuf, cs, slot = cpu_compress(codec, data, slot=SLOT); t2 = time.time()
-print("gen %.2fs cpu-compress %.2fs (%d threads) ratio %.4f" % (t1 - t0, t2 - t1, os.cpu_count(), cs.sum() / n))
-d_c = torch.from_numpy(cbuf).cuda(); d_s = torch.from_numpy(cs.view(np.int64)).cuda(); d_d = torch.from_numpy(data).cuda()
-out = torch.empty(n, dtype=torch.uint8, device="cuda"); res = torch.empty(len(cs), dtype=torch.int64, device="cuda")
-fn = fb.huf_decompress_batch if codec == "huf" else fb.fse_decompress_batch
-for _ in range(3):
-    fn(d_c, d_s, n, BLOCK, slot, out=out, results=res)
+L = fb.lib()
+BLOCK = 32768
+codec, op = what.split("_")
+src = torch.empty(n, dtype=torch.uint8, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+if codec == "u16":
+    L.FSEB200_genU16.restype = C.c_size_t; L.FSEB200_genU16.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_double, C.c_uint, C.c_void_p]
+    assert L.FSEB200_genU16(src.data_ptr(), n // 2, 0, 240, p, 1, st) == 0
+    SLOT = 32768; enc = lambda **k: fb.fseu16_compress_batch(src, BLOCK, SLOT, 0, 12, **k); dec = fb.fseu16_decompress_batch
+else:
+    L.FSEB200_probagen.restype = C.c_size_t; L.FSEB200_probagen.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p]
+    assert L.FSEB200_probagen(src.data_ptr(), n, 0, p, st) == 0
+    SLOT = fb.compress_bound(BLOCK)
+    e = fb.huf_compress_batch if codec == "huf" else fb.fse_compress_batch
+    enc = lambda **k: e(src, BLOCK, SLOT, 255, 12, **k); dec = fb.huf_decompress_batch if codec == "huf" else fb.fse_decompress_batch
+cbuf, cs = enc()
+out, res = dec(cbuf, cs, n, BLOCK, SLOT, orig=src)
 torch.cuda.synchronize()
-ok = bool((out == d_d).all()) and bool((res == torch.tensor([min(BLOCK, n - b * BLOCK) for b in range(len(cs))], device="cuda")).all())
+ok = bool(torch.equal(out, src))
+csum = int(cs.sum())
+run = (lambda: enc(cbuf=cbuf, csizes=cs)) if op == "enc" else (lambda: dec(cbuf, cs, n, BLOCK, SLOT, out=out, results=res, orig=src))
+for _ in range(3): run()
+torch.cuda.synchronize()
 ts = []
-for _ in range(10):
+for _ in range(iters):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(); fn(d_c, d_s, n, BLOCK, slot, out=out, results=res); e1.record(); torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-best = min(ts); med = sorted(ts)[len(ts) // 2]
-alg = n + int(cs.sum())
-print("%s %d MiB p=%.2f ok=%s best %.3f ms med %.3f ms -> %.1f GB/s uncompressed, %.1f GB/s algorithmic (%.1f%% of 6566)" %
-      (what, mib, p, ok, best, med, n / best / 1e6, alg / best / 1e6, alg / best / 1e6 / 65.66))
+    e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+best = min(ts); med = sorted(ts)[len(ts) // 2]; alg = n + csum
+print("%s %d MiB p=%.2f roundtrip_ok=%s ratio %.4f best %.3f ms med %.3f ms -> %.1f GB/s uncompressed, %.1f GB/s algorithmic (%.1f%% of 6566)" %
+      (what, mib, p, ok, csum / n, best, med, n / best / 1e6, alg / best / 1e6, alg / best / 1e6 / 65.66))
