@@ -12,16 +12,16 @@
 //   * one CTA = up to 64 consecutive blocks = 256 streams = 256 threads; a warp holds the SAME stream
 //     index of 32 DIFFERENT blocks, so the 32 lanes of a table look-up hit 32 different tables;
 //   * per-block decode tables are interleaved by column: u16 main[512][64] is indexed by the top 9
-//     bits of the bit window, u16 sub[256][64] by the top tableLog bits for the few windows that start
+//     bits of the bit window, u16 sub[192][64] by the top tableLog bits for the few windows that start
 //     a code longer than 9 bits (Huff0 numbers the longest codes from 0, so those windows are exactly
 //     the values below a per-block threshold T).  Column j of a row sits in bank j/2, and a warp holds
 //     the even (or the odd) columns, so every look-up is bank-conflict free whatever the 32 indices;
 //   * the choice main/sub is a select, not a branch: the hot loop has no divergent control flow;
 //   * each lane keeps a 64-bit left-aligned bit window in two registers; every two symbols a
-//     predicated block merges the next 32-bit word, taken from a private 8-word shared-memory ring the
-//     lane stages itself with aligned 16-byte global loads issued one iteration ahead of use;
+//     predicated block merges the next 32-bit word, taken from a private 16-word shared-memory ring the
+//     lane fills itself with cp.async (global -> shared, no register dependency, waited one visit later);
 //   * output: 8 symbols are packed into one 8-byte store per lane into its quarter of the block;
-//   * blocks whose long-code region exceeds 256 windows ("hard", e.g. near-flat 256-symbol alphabets),
+//   * blocks whose long-code region exceeds 192 windows ("hard", e.g. near-flat 256-symbol alphabets),
 //     unaligned segments and ragged tails take a slower per-symbol loop with a canonical-code search;
 //   * the grid is shaped so that every SM gets the same number of blocks per round (a round = 2 CTAs
 //     per SM): blocksPerCta is chosen <= 64 from the batch size, see launch_huf_decode().
@@ -35,15 +35,15 @@ constexpr int G = 64;             // block columns per CTA
 constexpr int THREADS = 4 * G;    // one lane per stream
 constexpr int MAIN_BITS = 9;
 constexpr int MAIN_ROWS = 1 << MAIN_BITS;
-constexpr int SUB_ROWS = 256;
-constexpr int RING = 8;           // 32-bit words of stream look-ahead per lane
+constexpr int SUB_ROWS = 192;
+constexpr int RING = 16;          // 32-bit words of stream look-ahead per lane
 constexpr u32 NOERR = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct __align__(16) Smem {
     u16 main[MAIN_ROWS][G];       // 64 KB   first-level table, column = block
-    u16 sub[SUB_ROWS][G];         // 32 KB   long-code windows (index < T); hard blocks park their sorted symbol list here
-    u32 ring[RING][THREADS];      //  8 KB   per-lane stream words (column = thread); table-build scratch before the streams start
+    u16 sub[SUB_ROWS][G];         // 24 KB   long-code windows (index < T); hard blocks park their sorted symbol list here
+    u32 ring[RING][THREADS];      // 16 KB   per-lane stream words (column = thread); table-build scratch before the streams start
     u16 rankEnd[HUF_MAX_TLOG + 2][G];   // end (exclusive) of weight w's range in tableLog-bit index space
     u16 listStart[HUF_MAX_TLOG + 2][G]; // first position of weight w in the sorted symbol list
     u16 longT[G];                 // number of tableLog-bit windows that start a code longer than 9 bits
@@ -127,7 +127,7 @@ __device__ void setup_block(Smem& sm, int blk, const u8* csrc, u64 csize, int wa
     if (T <= SUB_ROWS) {
         for (u32 idx = lane; idx < T; idx += 32) { u32 w = 1; sm.sub[idx][blk] = (u16)canon_lookup(sm, blk, idx, tl, w, list); }
     } else {
-        for (u32 k = lane; k < 256; k += 32) sm.sub[k][blk] = sorted[k];        // hard block: keep the code-ordered symbol list
+        for (u32 r = lane; r < 128; r += 32) sm.sub[r][blk] = (u16)(sorted[2 * r] | (sorted[2 * r + 1] << 8));   // hard block: park the code-ordered symbol list, 2 per cell
     }
     __syncwarp();
 }
@@ -178,28 +178,40 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     u8* outp = dst + (u64)b * g.blockSize + (u64)strm * seg;
     u32 hi = 0, lo = 0, nw = 0, r = 0, k = 0, q = 0;
     u64 chunkTop = 0, sBegin = 0;                    // address just above chunk 0 ; first byte of the stream
-    uint4 pend = make_uint4(0, 0, 0, 0);
     u32 const tl = sm.tlog[col];
 
-    auto chunk_addr = [&](u32 qq) -> u64 {           // aligned 16 bytes of chunk qq, clamped into the stream's own chunks (always readable)
-        u64 const lowest = sBegin & ~15ull;
-        u64 const a = chunkTop - 16ull * (qq + 1);
-        return (a < lowest || a >= chunkTop) ? lowest : a;
-    };
-    auto stage = [&](uint4 v, u32 qq) {              // chunk qq holds words 4qq..4qq+3 in descending address order; bytes below the stream read as 0
+    u32 fullChunks = 0;                              // chunks 0..fullChunks-1 lie entirely inside the stream (plain 16-byte copies)
+    u32 const ringLo = (u32)__cvta_generic_to_shared(&sm.ring[0][tid]);
+    // Chunk qq = the aligned 16 bytes ending at chunkTop - 16*qq; it holds stream words 4qq..4qq+3 in descending
+    // address order; bytes below the stream start read as 0 (the reference's reader pads the same way).
+    auto stage_sync = [&](u32 qq) {                  // boundary / out-of-stream chunks and the initial fill: through registers
         u64 const top = chunkTop - 16ull * qq;
-        if (top <= sBegin || 16ull * qq >= chunkTop) v = make_uint4(0, 0, 0, 0);
-        else if (top - 16 < sBegin) {
-            u32 const z = (u32)(sBegin - (top - 16));            // 1..15 leading bytes to clear
-            u32* p = reinterpret_cast<u32*>(&v);
-            #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                int const zb = (int)z - 4 * i;
-                if (zb >= 4) p[i] = 0; else if (zb > 0) p[i] &= 0xFFFFFFFFu << (8 * zb);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (top > sBegin && 16ull * qq < chunkTop) {
+            v = __ldg(reinterpret_cast<const uint4*>(top - 16));
+            if (top - 16 < sBegin) {
+                u32 const z = (u32)(sBegin - (top - 16));        // 1..15 leading bytes to clear
+                u32* p = reinterpret_cast<u32*>(&v);
+                #pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    int const zb = (int)z - 4 * i;
+                    if (zb >= 4) p[i] = 0; else if (zb > 0) p[i] &= 0xFFFFFFFFu << (8 * zb);
+                }
             }
         }
         u32 const s0 = (4 * qq) & (RING - 1);
         sm.ring[s0 + 0][tid] = v.w; sm.ring[s0 + 1][tid] = v.z; sm.ring[s0 + 2][tid] = v.y; sm.ring[s0 + 3][tid] = v.x;
+    };
+    auto stage_async = [&](u32 qq) {                 // steady state: global -> shared without touching registers (cp.async, 4 x 4 bytes)
+        u64 const top = chunkTop - 16ull * qq;
+        u32 const d0 = ringLo + ((4 * qq) & (RING - 1)) * (THREADS * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\t"
+                     "cp.async.ca.shared.global [%2], [%3], 4;\n\t"
+                     "cp.async.ca.shared.global [%4], [%5], 4;\n\t"
+                     "cp.async.ca.shared.global [%6], [%7], 4;\n\t"
+                     "cp.async.commit_group;"
+                     :: "r"(d0), "l"(top - 4), "r"(d0 + THREADS * 4), "l"(top - 8),
+                        "r"(d0 + 2 * THREADS * 4), "l"(top - 12), "r"(d0 + 3 * THREADS * 4), "l"(top - 16) : "memory");
     };
 
     if (live) {
@@ -248,9 +260,9 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
         u8 const last = pay[off + len - 1];
         u64 const e = sBegin + len;
         u32 const c0 = (u32)(8 * (chunkTop - e)) + (8 - hibit(last));      // garbage above the stream + zero padding + end mark
-        stage(__ldg(reinterpret_cast<const uint4*>(chunk_addr(0))), 0);
-        stage(__ldg(reinterpret_cast<const uint4*>(chunk_addr(1))), 1);
-        q = 2; pend = __ldg(reinterpret_cast<const uint4*>(chunk_addr(2)));
+        fullChunks = (u32)((chunkTop - ((sBegin + 15) & ~15ull)) >> 4);
+        stage_sync(0); stage_sync(1); stage_sync(2); stage_sync(3);
+        q = 4;
         k = c0 >> 5; r = c0 & 31;
         u32 const w0 = sm.ring[k & (RING - 1)][tid], w1 = sm.ring[(k + 1) & (RING - 1)][tid];
         nw = sm.ring[(k + 2) & (RING - 1)][tid];
@@ -260,18 +272,25 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     // ---- decode ----
     u32 const sMain = (u32)__cvta_generic_to_shared(&sm.main[0][col]);     // + row * 128
     u32 const sSub = (u32)__cvta_generic_to_shared(&sm.sub[0][col]);
-    u32 const ringLo = (u32)__cvta_generic_to_shared(&sm.ring[0][tid]);
     u32 const ringEnd = ringLo + RING * THREADS * 4;
     u32 rp = ringLo + ((k + 2) & (RING - 1)) * (THREADS * 4);              // slot `nw` was read from; a refill advances it first
     u32 const T = sm.longT[col];
     u32 const shTl = 32 - (tl ? tl : 1);
     bool const hardBlk = sm.hard[col] != 0;
 
-    auto top_up = [&]() {                             // keep the ring ahead of the consumer (at most one chunk per 8 symbols)
-        if (4 * q <= k + 7) {
-            stage(pend, q); q++;
-            pend = __ldg(reinterpret_cast<const uint4*>(chunk_addr(q)));    // consumed no earlier than the next call
+    // Keep the ring ahead of the consumer.  Called at least every 16 symbols (<= 6 words consumed); a chunk is
+    // staged when its 4 slots are free (4q <= k+15), so afterwards 4q >= k+12: the newest chunk is never needed
+    // before the next call, which is why waiting for all copies but the newest one is enough.
+    auto top_up = [&]() {
+        #pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (4 * q <= k + 15) {
+                if (q < fullChunks) stage_async(q); else stage_sync(q);
+                q++;
+            }
         }
+        if (q >= fullChunks) asm volatile("cp.async.wait_group 0;" ::: "memory");   // tail of the stream: chunks come through registers, nothing may stay pending
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
     };
     // one symbol, branch-free: E = nbBits | symbol << 8, window advanced
 #define HUFD_LOOKUP(E) do { \
@@ -302,7 +321,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     if (fastOk) {
         u32 const nIter = segLen >> 3;
         for (u32 it = 0; it < nIter; it++) {
-            top_up();
+            if ((it & 1) == 0) top_up();
             u32 o0, o1, e0, e1;
             HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
             o0 = __byte_perm(e0, e1, 0x0051);                       // {sym0, sym1, x, x}
@@ -318,7 +337,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     }
     // ragged tails, unaligned segments and hard blocks: one symbol at a time
     {
-        auto parked = [&](u32 kk) -> u32 { return sm.sub[kk][col] & 0xFFu; };
+        auto parked = [&](u32 kk) -> u32 { return (sm.sub[kk >> 1][col] >> (8 * (kk & 1))) & 0xFFu; };
         while (pos < segLen) {
             if ((pos & 7) == 0) top_up();
             u32 e;
@@ -336,6 +355,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
 #undef HUFD_LOOKUP
 #undef HUFD_REFILL
 
+    asm volatile("cp.async.wait_all;" ::: "memory");
     // ---- verdict: every stream must be consumed exactly (huf_decompress.c:348-349) ----
     if (go) {
         u64 const consumed = 32ull * k + (r & 31);

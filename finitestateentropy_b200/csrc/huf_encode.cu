@@ -18,11 +18,11 @@
 //      whole CTA behind one lane (the first version did that: 88% of its stalls were barrier waits).
 //      Output: a 1.25 KB "plan" per block in a stream-ordered scratch buffer (code table, header,
 //      verdict).
-//   2. huf_emit_kernel, ONE CTA PER BLOCK, no serial section: the block is staged once into shared
-//      memory; a Huff0 stream is the concatenation, last symbol first, of the codes, so every thread
-//      owns a run of symbols, an exclusive scan of the run bit-lengths gives its bit offset, and it ORs
-//      its codes into a shared-memory image of the whole compressed block, copied out with aligned
-//      16-byte stores (image and destination share their alignment mod 16).
+//   2. huf_emit_kernel, ONE CTA (4 warps) PER BLOCK, one warp per stream, no serial section and no
+//      second look at the data: stream sizes and offsets are already known from the per-segment
+//      histograms of the plan kernel.  (An earlier version gave each thread a contiguous run of
+//      symbols staged in shared memory: runs are 128 bytes apart, i.e. all 32 lanes of a warp in the
+//      same bank -- 525M bank conflicts per 256 MiB, short-scoreboard 38 stalls per issue.)
 #include "common.cuh"
 #include "fse_dev.cuh"
 #include "sink_dev.cuh"
@@ -37,15 +37,18 @@ struct __align__(16) Plan {        // per block, in global scratch
     u32 ctable[256];               // val | nbBits << 16
     u8  header[136];
     u32 hSize;
-    u32 state;                     // 0 = emit, 1 = verdict is final
-    u64 verdict;
+    u32 state;                     // 0 = emit, 1 = verdict is final (nothing to emit)
+    u32 total;                     // compressed size when state == 0
+    u32 streamOff[4];              // byte offset of each stream from the start of the block
+    u32 streamBytes[4];
 };
 
 // ---------------------------------------------------------------------------------------------
-// kernel 1: statistics, code table, tree header -- one warp per block
+// kernel 1: statistics, code table, tree header, stream sizes, verdict -- one warp per block
 // ---------------------------------------------------------------------------------------------
 constexpr int PLAN_WARPS = 8;
 struct PlanWarp {
+    u32   count4[4][256];          // one histogram per stream: stream sizes follow from them without touching the data again
     u32   count[256];
     HNode nodes[2 * 256 + 2];
     u32   ctable[256];
@@ -54,6 +57,41 @@ struct PlanWarp {
     u8    header[136];
     u32   wksp[384];
 };
+
+// histogram of src[begin, end) into cnt[256] (shared memory), one warp
+__device__ __forceinline__ void warp_hist_range(u32* cnt, const u8* s, u32 begin, u32 end, unsigned lane)
+{
+    u32 i = begin;
+    u32 const head = min(end, (u32)((begin + 15) & ~15u));         // bytes up to 16-byte alignment of the OFFSET ...
+    bool const vec = ((reinterpret_cast<u64>(s) & 15) == 0);       // ... which is alignment of the address when the block is aligned
+    if (vec) {
+        for (u32 k = i + lane; k < head; k += 32) atomicAdd(&cnt[s[k]], 1u);
+        i = head;
+        u32 const nvec = (end - i) / 16;
+        const uint4* const gv = reinterpret_cast<const uint4*>(s + i);
+        for (u32 v0 = 0; v0 < nvec; v0 += 64) {                    // two loads in flight per lane
+            u32 const va = v0 + lane, vb = v0 + 32 + lane;
+            uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
+            if (va < nvec) xa = __ldg(gv + va);
+            if (vb < nvec) xb = __ldg(gv + vb);
+            #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if ((h == 0 ? va : vb) >= nvec) continue;
+                uint4 const v = h == 0 ? xa : xb;
+                u32 const wd[4] = { v.x, v.y, v.z, v.w };
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 const x = wd[k];
+                    u32 const b0 = x & 0xFF, b1 = (x >> 8) & 0xFF, b2 = (x >> 16) & 0xFF, b3 = x >> 24;
+                    if ((b0 == b1) & (b1 == b2) & (b2 == b3)) atomicAdd(&cnt[b0], 4u);
+                    else { atomicAdd(&cnt[b0], 1u); atomicAdd(&cnt[b1], 1u); atomicAdd(&cnt[b2], 1u); atomicAdd(&cnt[b3], 1u); }
+                }
+            }
+        }
+        i += nvec * 16;
+    }
+    for (u32 k = i + lane; k < end; k += 32) atomicAdd(&cnt[s[k]], 1u);
+}
 
 __global__ void __launch_bounds__(32 * PLAN_WARPS)
 huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
@@ -69,7 +107,7 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     u8* const d = cbuf + (u64)b * g.slot;
     u64 const cap = g.slot;
     Plan& P = plans[b];
-#define FSEB_FINAL(v) do { if (lane == 0) { P.state = 1; P.verdict = (v); csizes[b] = (v); } return; } while (0)
+#define FSEB_FINAL(v) do { if (lane == 0) { P.state = 1; csizes[b] = (v); } return; } while (0)
 
     // argument checks of HUF_compress_internal (huf_compress.c:656-664), in its order
     if (!n) FSEB_FINAL(0);
@@ -80,34 +118,25 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     unsigned const msvDecl = msvReq ? msvReq : HUF_MAX_SV;
     unsigned huffLog = tlogReq ? tlogReq : HUF_DEF_TLOG;
 
-    // ---- histogram (HIST_count_wksp semantics, hist.c:163-173,128) ----
-    for (u32 i = lane; i < 256; i += 32) w.count[i] = 0;
+    // ---- histograms, one per 4X segment (HIST_count_wksp semantics for their sum, hist.c:163-173,128) ----
+    u32 const seg = (n + 3) / 4;
+    for (u32 i = lane; i < 4 * 256; i += 32) (&w.count4[0][0])[i] = 0;
     __syncwarp();
-    {
-        u32 done = 0;
-        if ((reinterpret_cast<u64>(s) & 15) == 0) {
-            u32 const nvec = n / 16;
-            const uint4* const gv = reinterpret_cast<const uint4*>(s);
-            for (u32 i = lane; i < nvec; i += 32) {
-                uint4 const v = __ldg(gv + i);
-                u32 const wd[4] = { v.x, v.y, v.z, v.w };
-                #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    u32 const x = wd[k];
-                    u32 const b0 = x & 0xFF, b1 = (x >> 8) & 0xFF, b2 = (x >> 16) & 0xFF, b3 = x >> 24;
-                    if ((b0 == b1) & (b1 == b2) & (b2 == b3)) atomicAdd(&w.count[b0], 4u);
-                    else { atomicAdd(&w.count[b0], 1u); atomicAdd(&w.count[b1], 1u); atomicAdd(&w.count[b2], 1u); atomicAdd(&w.count[b3], 1u); }
-                }
-            }
-            done = nvec * 16;
-        }
-        for (u32 i = done + lane; i < n; i += 32) atomicAdd(&w.count[s[i]], 1u);
+    #pragma unroll 1
+    for (u32 k = 0; k < 4; k++) {
+        u32 const beg = min(k * seg, n), end = (k < 3) ? min((k + 1) * seg, n) : n;
+        warp_hist_range(w.count4[k], s, beg, end, lane);
     }
     __syncwarp();
     u32 top = 0, best = 0;
-    for (u32 i = lane; i < 256; i += 32) { u32 const c = w.count[i]; if (c) top = i; best = c > best ? c : best; }
+    for (u32 i = lane; i < 256; i += 32) {
+        u32 const c = w.count4[0][i] + w.count4[1][i] + w.count4[2][i] + w.count4[3][i];
+        w.count[i] = c;
+        if (c) top = i; best = c > best ? c : best;
+    }
     #pragma unroll
     for (int dlt = 16; dlt; dlt >>= 1) { top = max(top, __shfl_xor_sync(FULL, top, dlt)); best = max(best, __shfl_xor_sync(FULL, best, dlt)); }
+    __syncwarp();
     if (msvDecl < 255 && top > msvDecl) FSEB_FINAL(err(E_MSV_TOO_SMALL));                         // hist.c:128
     if (best == n) { if (lane == 0) d[0] = s[0]; FSEB_FINAL(1); }                                // huf_compress.c:673
     if (best <= (n >> 7) + 4) FSEB_FINAL(0);                                                      // :674
@@ -125,134 +154,124 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     hs = __shfl_sync(FULL, hs, 0);
     if (is_err(hs)) FSEB_FINAL(hs);
     if (hs + 12 >= n) FSEB_FINAL(0);
-    if (cap - hs < 6 + 1 + 1 + 1 + 8 || n < 12) FSEB_FINAL(0);                                    // :564-565
+    u64 const capLeft = cap - hs;
+    if (capLeft < 6 + 1 + 1 + 1 + 8 || n < 12) FSEB_FINAL(0);                                     // :564-565
+    // ---- stream sizes from the per-segment histograms; the writer's capacity rule stream after stream
+    //      (:566-600, bitstream.h:190,246,258) and the final compressibility test (:625) ----
+    u32 bits[4];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 acc = 0;
+        for (u32 i = lane; i <= msv; i += 32) acc += w.count4[k][i] * (w.ctable[i] >> 16);
+        #pragma unroll
+        for (int dlt = 16; dlt; dlt >>= 1) acc += __shfl_xor_sync(FULL, acc, dlt);
+        bits[k] = acc;
+    }
+    u64 op = 6; bool fits = true;
+    u32 offs[4], lens[4];
+    #pragma unroll
+    for (int t = 0; t < 4; t++) {
+        u64 const capk = capLeft - op;
+        u64 const tot = (u64)bits[t] + 1;                                    // + end mark
+        if (fits && (capk <= 8 || (tot >> 3) >= capk - 8)) fits = false;
+        offs[t] = (u32)(hs + op); lens[t] = (u32)((tot + 7) >> 3);
+        op += lens[t];
+    }
+    u64 const total = hs + op;
+    if (!fits || total >= (u64)n - 1) FSEB_FINAL(0);
     __syncwarp();
     for (u32 i = lane; i < 256; i += 32) P.ctable[i] = w.ctable[i];
     for (u32 i = lane; i < (u32)hs; i += 32) P.header[i] = w.header[i];
-    if (lane == 0) { P.hSize = (u32)hs; P.state = 0; P.verdict = 0; }
+    if (lane < 4) { P.streamOff[lane] = offs[lane]; P.streamBytes[lane] = lens[lane]; }
+    if (lane == 0) { P.hSize = (u32)hs; P.state = 0; P.total = (u32)total; csizes[b] = total; }
 #undef FSEB_FINAL
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 2: emit -- one CTA per block, everything parallel
+// kernel 2: emit -- one CTA (4 warps) per block, one warp per stream, no serial section.
+// A stream is the concatenation, last symbol first, of the codes.  The warp walks its segment from the
+// end in groups of 128 symbols: lane l takes the 4 symbols just below hi-4l (coalesced global read,
+// nothing staged), concatenates their codes (<= 48 bits), a warp scan of the lengths gives its bit
+// offset, and it ORs the bits into the shared-memory image of the compressed block at the final
+// position of the stream (known from the plan).  Then the image is copied out with aligned 16-byte
+// stores (image and destination share their alignment mod 16).
 // ---------------------------------------------------------------------------------------------
-constexpr int THREADS = 256;
+constexpr int THREADS = 128;
 
-struct EmitShared {
-    u32 ctable[256];
-    u32 chunkBits[THREADS];
-    u32 chunkOff[THREADS];
-    u32 streamBytes[4];
-    u32 streamOff[4];
-    u32 flag, total;
-};
-
-template <bool STAGED>
 __global__ void __launch_bounds__(THREADS)
-huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
-                const Plan* __restrict__ plans, u32 stageBytes)
+huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EmitShared& sh = *reinterpret_cast<EmitShared*>(smem_raw);
-    u8* const srcStage = smem_raw + ((sizeof(EmitShared) + 15) & ~(size_t)15);
-    u32* const image = reinterpret_cast<u32*>(srcStage + stageBytes);
+    u32* const ctab = reinterpret_cast<u32*>(smem_raw);             // 256 cells
+    u32* const image = ctab + 256;
     int const tid = threadIdx.x;
+    unsigned const lane = tid & 31u; int const k = tid >> 5;
     u32 const b = blockIdx.x;
     const Plan& P = plans[b];
     if (P.state != 0) return;                                       // verdict already delivered by the plan kernel
     u32 const n = block_len(g, b);
     const u8* const s = src + (u64)b * g.blockSize;
     u8* const d = cbuf + (u64)b * g.slot;
-    u64 const cap = g.slot;
-    u32 const hSize = P.hSize;
-    u64 const capLeft = cap - hSize;
+    u32 const hSize = P.hSize, total = P.total;
+    u32 const al = (u32)(reinterpret_cast<u64>(d) & 15);            // image byte i <-> d[i - al]
+    u32 const imgWords = (al + total + 3) / 4 + 2;
 
-    sh.ctable[tid] = P.ctable[tid];
-    if (tid == 0) sh.flag = 0;
-    if (STAGED) {                                                   // HBM/L2 -> shared, once
-        if ((reinterpret_cast<u64>(s) & 15) == 0) {
-            u32 const nvec = n / 16;
-            const uint4* const gv = reinterpret_cast<const uint4*>(s);
-            uint4* const sv = reinterpret_cast<uint4*>(srcStage);
-            for (u32 i = tid; i < nvec; i += THREADS) sv[i] = __ldg(gv + i);
-            for (u32 i = nvec * 16 + tid; i < n; i += THREADS) srcStage[i] = s[i];
-        } else {
-            for (u32 i = tid; i < n; i += THREADS) srcStage[i] = s[i];
-        }
-    }
-    __syncthreads();
-    auto sym = [&](u32 i) -> u32 { return STAGED ? (u32)srcStage[i] : (u32)s[i]; };
-
-    // ---- pass A: bit length of every thread's run; stream k is owned by threads 64k..64k+63 ----
-    u32 const seg = (n + 3) / 4;
-    int const k = tid >> 6, j = tid & 63;
-    u32 const segBeg = (u32)k * seg;
-    u32 const segEnd = (k < 3) ? segBeg + seg : n;
-    u32 const segLen = segEnd - segBeg;
-    u32 const run = (segLen + 63) / 64;
-    u32 const offHi = min((u32)j * run, segLen), offLo = min((u32)(j + 1) * run, segLen);
-    u32 const hiC = segEnd - offHi, loIdx = segEnd - offLo;        // this thread's run = symbols [loIdx, hiC), emitted high to low
-    {   u32 bits = 0;
-        for (u32 i = loIdx; i < hiC; i++) bits += sh.ctable[sym(i)] >> 16;
-        sh.chunkBits[tid] = bits;
-    }
-    __syncthreads();
-    {   // exclusive scan over the 64 runs of each stream (2 warps per stream)
-        u32 const v = sh.chunkBits[tid];
-        u32 incl = v;
-        unsigned const lane = tid & 31;
-        #pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) { u32 const t = __shfl_up_sync(FULL, incl, dd); if (lane >= (unsigned)dd) incl += t; }
-        if (lane == 31) sh.chunkOff[tid] = incl;                    // warp total, parked in its last slot
-        __syncthreads();
-        u32 const firstHalf = sh.chunkOff[64 * k + 31];
-        u32 const base = (j >= 32) ? firstHalf : 0u;
-        u32 const total = firstHalf + sh.chunkOff[64 * k + 63];
-        __syncthreads();
-        sh.chunkOff[tid] = base + incl - v;
-        if (j == 0) sh.streamBytes[k] = total;                      // bits for now
-    }
-    __syncthreads();
-    if (tid == 0) {                                // sizes with the writer's capacity rule, stream after stream (:566-600, bitstream.h:190,246,258)
-        u64 op = 6; bool fits = true;
-        for (int t = 0; t < 4 && fits; t++) {
-            u64 const capk = capLeft - op;
-            u64 const tot = (u64)sh.streamBytes[t] + 1;                       // + end mark
-            if (capk <= 8 || (tot >> 3) >= capk - 8) { fits = false; break; }
-            sh.streamOff[t] = (u32)op;
-            sh.streamBytes[t] = (u32)((tot + 7) >> 3);
-            op += sh.streamBytes[t];
-        }
-        u64 const total = hSize + op;
-        if (!fits || total >= (u64)n - 1) { sh.flag = 1; csizes[b] = 0; }                            // :625
-        else sh.total = (u32)total;
-    }
-    __syncthreads();
-    if (sh.flag) return;
-    u32 const total = sh.total;
-
-    // ---- pass B: build the block image in shared memory ----
-    u32 const al = (u32)(reinterpret_cast<u64>(d) & 15);          // image byte i <-> d[i - al]
-    u32 const imgWords = (al + total + 3) / 4 + 1;
+    ctab[tid] = P.ctable[tid]; ctab[tid + 128] = P.ctable[tid + 128];
     for (u32 i = tid; i < imgWords; i += THREADS) image[i] = 0;
     __syncthreads();
     {   u8* const img8 = reinterpret_cast<u8*>(image);
         for (u32 i = tid; i < hSize; i += THREADS) img8[al + i] = P.header[i];
-        if (tid < 3) { u32 const v = sh.streamBytes[tid]; img8[al + hSize + 2 * tid] = (u8)v; img8[al + hSize + 2 * tid + 1] = (u8)(v >> 8); }
+        if (tid < 3) { u32 const v = P.streamBytes[tid]; img8[al + hSize + 2 * tid] = (u8)v; img8[al + hSize + 2 * tid + 1] = (u8)(v >> 8); }
     }
     __syncthreads();
-    {   u64 const Pb = 8ull * (al + hSize + sh.streamOff[k]) + sh.chunkOff[tid];
-        u32* wp = image + (Pb >> 5);
-        unsigned held = (unsigned)(Pb & 31);
-        u64 acc = 0;
-        for (u32 i = hiC; i-- > loIdx;) {
-            u32 const e = sh.ctable[sym(i)];
-            acc |= (u64)(e & 0xFFFF) << held;
-            held += e >> 16;
-            if (held >= 32) { atomicOr(wp++, (u32)acc); acc >>= 32; held -= 32; }
+    {
+        u32 const seg = (n + 3) / 4;
+        int const segBeg = (int)(k * seg);
+        int const segEnd = (k < 3) ? (int)((k + 1) * seg) : (int)n;
+        u64 bitpos = 8ull * (al + P.streamOff[k]);
+        auto fetch = [&](int hi) -> u32 {                           // the 4 symbols below hi-4*lane, highest index in the low byte; 0xFF.. never used when invalid
+            int const top = hi - 4 * (int)lane;                     // exclusive
+            u32 v = 0;
+            if (top - 4 >= segBeg && ((reinterpret_cast<u64>(s + top) & 3) == 0)) {
+                u32 const x = __ldg(reinterpret_cast<const u32*>(s + top - 4));
+                v = __byte_perm(x, 0, 0x0123);                      // reverse: byte0 = s[top-1]
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 4; j++) { int const i = top - 1 - j; if (i >= segBeg) v |= (u32)s[i] << (8 * j); }
+            }
+            return v;
+        };
+        u32 nxt = (segEnd > segBeg) ? fetch(segEnd) : 0;
+        for (int hi = segEnd; hi > segBeg; hi -= 128) {
+            u32 const cur = nxt;
+            if (hi - 128 > segBeg) nxt = fetch(hi - 128);           // next group's load in flight while this one is packed
+            int const top = hi - 4 * (int)lane;
+            u64 acc = 0; u32 held = 0;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (top - 1 - j >= segBeg) {
+                    u32 const e = ctab[(cur >> (8 * j)) & 0xFF];
+                    acc |= (u64)(e & 0xFFFF) << held;
+                    held += e >> 16;
+                }
+            }
+            u32 incl = held;
+            #pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { u32 const t = __shfl_up_sync(FULL, incl, dd); if (lane >= (unsigned)dd) incl += t; }
+            u32 const sum = __shfl_sync(FULL, incl, 31);
+            if (held) {
+                u64 const at = bitpos + (incl - held);
+                u32* const wp = image + (at >> 5);
+                u32 const sh = (u32)(at & 31);
+                u32 const a0 = (u32)acc, a1 = (u32)(acc >> 32);
+                u32 const w0 = a0 << sh, w1 = __funnelshift_l(a0, a1, sh), w2 = __funnelshift_l(a1, 0, sh);
+                if (w0) atomicOr(wp, w0);
+                if (w1) atomicOr(wp + 1, w1);
+                if (w2) atomicOr(wp + 2, w2);
+            }
+            bitpos += sum;
         }
-        if (loIdx == segBeg && hiC > loIdx) { acc |= 1ull << held; held++; if (held >= 32) { atomicOr(wp++, (u32)acc); acc >>= 32; held -= 32; } }   // end mark by the owner of the first symbol
-        if (held) atomicOr(wp, (u32)acc);
+        if (lane == 0) atomicOr(image + (bitpos >> 5), 1u << (bitpos & 31));      // end mark (bitstream.h:256)
     }
     __syncthreads();
     // ---- copy out (HBM write) ----
@@ -269,7 +288,6 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
             for (u32 i = first16 + nvec * 16 + tid; i < endOff; i += THREADS) d[i - al] = img8[i];
         }
     }
-    if (tid == 0) csizes[b] = total;
 }
 
 }  // namespace hufe
@@ -292,19 +310,14 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
         unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
         hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans);
     }
-    {   bool const staged = g.blockSize <= 65536;                                              // 2 x 128 KB would not fit in 227 KB
-        u32 const stageBytes = staged ? ((g.blockSize + 15u + 16u) & ~15u) : 0u;
-        size_t const imageBytes = (size_t)g.blockSize + 64 + 16;                               // accepted blocks are < n bytes
-        size_t const smem = ((sizeof(hufe::EmitShared) + 15) & ~(size_t)15) + stageBytes + imageBytes + 16;
-        static size_t configured[2] = { 0, 0 };
-        if (smem > configured[staged]) {
-            e = staged ? cudaFuncSetAttribute(hufe::huf_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                       : cudaFuncSetAttribute(hufe::huf_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {   size_t const smem = 256 * sizeof(u32) + (size_t)g.blockSize + 64 + 16 + 16;           // code table + image (accepted blocks are < n bytes)
+        static size_t configured = 0;
+        if (smem > configured) {
+            e = cudaFuncSetAttribute(hufe::huf_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured[staged] = smem;
+            configured = smem;
         }
-        if (staged) hufe::huf_emit_kernel<true><<<g.nBlocks, hufe::THREADS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, plans, stageBytes);
-        else hufe::huf_emit_kernel<false><<<g.nBlocks, hufe::THREADS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, plans, stageBytes);
+        hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, smem, stream>>>(g, (u8*)cbuf, (const u8*)src, plans);
     }
     e = cudaGetLastError();
     cudaError_t const e2 = cudaFreeAsync(plans, stream);
