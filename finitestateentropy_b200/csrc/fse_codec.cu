@@ -26,6 +26,7 @@ namespace fsek {
 constexpr int WARPS = 4;
 constexpr int THREADS = 32 * WARPS;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr u32 WIN = 512;          // bytes of compressed stream staged per warp (decode)
 
 // ---- warp-cooperative symbol spreading ------------------------------------------------------
 // Visit v (0..size-1) of the reference walk lands on cell (v*stride) & mask; cells above `high`
@@ -69,126 +70,194 @@ template <> struct DecCfg<false> { static constexpr unsigned MSV = FSE_MAX_SV, T
 template <> struct DecCfg<true>  { static constexpr unsigned MSV = U16_MAX_SV, TL = U16_MAX_TLOG, CELLS = 1u << U16_MAX_TLOG; };
 
 template <bool WIDE>
-struct DecWarp {
+struct alignas(16) DecWarp {
     u32   dt[1 + DecCfg<WIDE>::CELLS];
     short norm[DecCfg<WIDE>::MSV + 1];
     u16   cum[DecCfg<WIDE>::MSV + 3];
     u16   nextOf[DecCfg<WIDE>::MSV + 1];
-    u64   ret;
+    alignas(16) u64 win[WIN / 8 + 2];
 };
 
-// unaligned 64-bit little-endian read of stream bytes [at, at+8) from global memory: two aligned loads
-__device__ __forceinline__ u64 ld64_global(const u8* p)
+// The compressed stream is consumed through a 512-byte shared-memory window that the whole warp refills
+// with one coalesced 16-byte load per lane (the first version let lane 0 fetch its 8-byte container from
+// global memory on every reload: with 200+ KB of shared memory in use the L1 is tiny, every reload went
+// to L2 -- 128 cycles per symbol).  Lane 0 then reads its container with two aligned LDS.64.
+struct WSrc {                       // reader state, meaningful on lane 0
+    u64 base;                       // absolute address of stream byte 0
+    u64 len; u64 at; u64 w; unsigned used;
+    u64 winBase;                    // absolute address (16-aligned) of window byte 0
+    const u64* win;                 // shared memory, WIN/8 + 1 words
+};
+__device__ __forceinline__ u64 ws_ld64(const WSrc& b, u64 at)
 {
-    u64 const a = reinterpret_cast<u64>(p);
-    const u64* const q = reinterpret_cast<const u64*>(a & ~7ull);
-    unsigned const sh = (unsigned)(a & 7) * 8;
-    u64 const lo = __ldg(q);
+    u32 const o = (u32)(b.base + at - b.winBase);
+    u32 const sh = (o & 7) * 8;
+    u64 const lo = b.win[o >> 3];
     if (sh == 0) return lo;
-    u64 const hi = __ldg(q + 1);
-    return (lo >> sh) | (hi << (64 - sh));
+    return (lo >> sh) | (b.win[(o >> 3) + 1] << (64 - sh));
 }
-
-// Backward bit reader with the reference's exact reload semantics (lib/bitstream.h:272-448); the
-// 64-bit container is fetched with aligned global loads.
-struct GSrc { const u8* s; u64 len; u64 at; u64 w; unsigned used; };
-__device__ inline u64 gs_open(GSrc& b, const u8* p, u64 len)
+// warp-wide: make the window cover [at - margin, at + 8) ; call with `at` broadcast from lane 0
+__device__ __forceinline__ void ws_slide(WSrc& b, u64 at, u64* win, bool force)
 {
-    b.s = p; b.len = len; b.at = 0; b.w = 0; b.used = 0;
+    u64 const lowest = b.base & ~15ull;
+    u64 const pos = b.base + at;
+    if (!force && (pos >= b.winBase + 64 || b.winBase <= lowest) && pos + 8 <= b.winBase + WIN) return;     // still covered (warp-uniform)
+    u64 nb = ((pos + 8 + 15) & ~15ull) - WIN;
+    if (nb < lowest || nb > pos) nb = lowest;                       // short streams / wrap
+    u64 const endAddr = (b.base + b.len + 15) & ~15ull;             // never read past the 16-byte envelope of the stream
+    unsigned const lane = lane_id();
+    u64 const a = nb + 16ull * lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (a < endAddr) v = __ldg(reinterpret_cast<const uint4*>(a));
+    __syncwarp();
+    reinterpret_cast<uint4*>(win)[lane] = v;
+    if (lane == 0) win[WIN / 8] = 0;
+    b.winBase = nb;
+    __syncwarp();
+}
+__device__ inline u64 ws_open(WSrc& b, u64 len)                    // bitstream.h:272-318 ; window already covers the end of the stream
+{
+    b.len = len; b.at = 0; b.w = 0; b.used = 0;
     if (len < 1) return err(E_SRC_WRONG);
     if (len >= 8) {
-        b.at = len - 8; b.w = ld64_global(p + b.at);
+        b.at = len - 8; b.w = ws_ld64(b, b.at);
         u32 const last = (u32)(b.w >> 56);
         if (last == 0) return err(E_GENERIC);
         b.used = 8 - hibit(last);
     } else {
-        b.w = p[0];
-        for (u64 i = 1; i < len; i++) b.w += (u64)p[i] << (8 * i);
-        if (p[len - 1] == 0) return err(E_CORRUPT);
-        b.used = 8 - hibit(p[len - 1]);
+        u64 const x = ws_ld64(b, 0) & ((1ULL << (8 * len)) - 1);   // bytes 0..len-1, byte i at bits 8i (as the reference assembles them)
+        b.w = x;
+        u32 const last = (u32)(x >> (8 * (len - 1))) & 0xFF;
+        if (last == 0) return err(E_CORRUPT);
+        b.used = 8 - hibit(last);
         b.used += (unsigned)(8 - len) * 8;
     }
     return len;
 }
-__device__ __forceinline__ u64 gs_read(GSrc& b, unsigned nb)
+__device__ __forceinline__ u64 ws_read(WSrc& b, unsigned nb)
 {
     u64 const mask = nb ? ((1ULL << nb) - 1) : 0;
     u64 const v = (b.w >> ((64u - b.used - nb) & 63u)) & mask;
     b.used += nb; return v;
 }
-__device__ __forceinline__ u64 gs_read_fast(GSrc& b, unsigned nb)
+__device__ __forceinline__ u64 ws_read_fast(WSrc& b, unsigned nb)
 {
     u64 const v = (b.w << (b.used & 63u)) >> ((64u - nb) & 63u);
     b.used += nb; return v;
 }
-__device__ __forceinline__ int gs_refill(GSrc& b)
+__device__ __forceinline__ int ws_refill(WSrc& b)                  // bitstream.h:416-440
 {
     if (b.used > 64) return SRC_OVER;
-    if (b.at >= 8) { b.at -= b.used >> 3; b.used &= 7; b.w = ld64_global(b.s + b.at); return SRC_MORE; }
+    if (b.at >= 8) { b.at -= b.used >> 3; b.used &= 7; b.w = ws_ld64(b, b.at); return SRC_MORE; }
     if (b.at == 0) return b.used < 64 ? SRC_ENDBUF : SRC_DONE;
     u64 nb = b.used >> 3; int st = SRC_MORE;
     if (b.at < nb) { nb = b.at; st = SRC_ENDBUF; }
-    b.at -= nb; b.used -= (unsigned)nb * 8; b.w = ld64_global(b.s + b.at);
+    b.at -= nb; b.used -= (unsigned)nb * 8; b.w = ws_ld64(b, b.at);
     return st;
 }
 
 template <bool FAST>
-__device__ __forceinline__ u32 dstep(u32& state, GSrc& b, const u32* cells)
+__device__ __forceinline__ u32 dstep(u32& state, WSrc& b, const u32* cells)
 {
     u32 const cell = cells[state];
     u32 const nb = cell >> 24;
-    u32 const low = (u32)(FAST ? gs_read_fast(b, nb) : gs_read(b, nb));
+    u32 const low = (u32)(FAST ? ws_read_fast(b, nb) : ws_read(b, nb));
     state = (cell & 0xFFFF) + low;
     return (cell >> 16) & 0xFF;
 }
 
-// FSE_decompress_usingDTable_generic (fse_decompress.c:178-238), lane 0 only.
+// FSE_decompress_usingDTable_generic (fse_decompress.c:178-238).  The chain runs on lane 0 in batches of
+// up to 8 loop iterations (<= 48 stream bytes); between batches the warp slides the window.  Returns on all lanes.
 template <bool FAST>
-__device__ inline u64 lane_decode_bytes(u8* out, u64 cap, const u8* cSrc, u64 cSize, const u32* dt)
+__device__ inline u64 warp_decode_bytes(u8* out, u64 cap, const u8* cSrc, u64 cSize, const u32* dt, u64* win)
 {
+    unsigned const lane = lane_id();
     unsigned const tl = dt[0] & 0xFFFF;
     const u32* const cells = dt + 1;
     long long const omax = (long long)cap;
     long long op = 0;
-    GSrc b;
-    {   u64 const e = gs_open(b, cSrc, cSize); if (is_err(e)) return e; }
-    u32 s1 = (u32)gs_read(b, tl); gs_refill(b);
-    u32 s2 = (u32)gs_read(b, tl); gs_refill(b);
+    WSrc b; b.base = reinterpret_cast<u64>(cSrc); b.len = cSize; b.winBase = 0; b.win = win; b.at = 0; b.w = 0; b.used = 0;
+    u32 s1 = 0, s2 = 0;
+    u64 ret = 0; int phase = 0;                                    // 0 = main loop, 1 = tail, 2 = finished
+    ws_slide(b, cSize >= 8 ? cSize - 8 : 0, win, true);
+    if (lane == 0) {
+        u64 const e = ws_open(b, cSize);
+        if (is_err(e)) { ret = e; phase = 2; }
+        else {
+            s1 = (u32)ws_read(b, tl); ws_refill(b);
+            s2 = (u32)ws_read(b, tl); ws_refill(b);
+        }
+    }
     bool const al4 = (reinterpret_cast<u64>(out) & 3) == 0;
-    for (; (gs_refill(b) == SRC_MORE) & (op < omax - 3); op += 4) {
-        u32 const a0 = dstep<FAST>(s1, b, cells), a1 = dstep<FAST>(s2, b, cells);
-        u32 const a2 = dstep<FAST>(s1, b, cells), a3 = dstep<FAST>(s2, b, cells);
-        if (al4) *reinterpret_cast<u32*>(out + op) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
-        else { out[op] = (u8)a0; out[op + 1] = (u8)a1; out[op + 2] = (u8)a2; out[op + 3] = (u8)a3; }
-    }
     for (;;) {
-        if (op > omax - 2) return err(E_DST_TOO_SMALL);
-        out[op++] = (u8)dstep<FAST>(s1, b, cells);
-        if (gs_refill(b) == SRC_OVER) { out[op++] = (u8)dstep<FAST>(s2, b, cells); break; }
-        if (op > omax - 2) return err(E_DST_TOO_SMALL);
-        out[op++] = (u8)dstep<FAST>(s2, b, cells);
-        if (gs_refill(b) == SRC_OVER) { out[op++] = (u8)dstep<FAST>(s1, b, cells); break; }
+        phase = __shfl_sync(FULL, phase, 0);
+        if (phase == 2) break;
+        u64 const at = __shfl_sync(FULL, b.at, 0);
+        ws_slide(b, at, win, false);
+        if (lane == 0) {
+            if (phase == 0) {
+                int it = 0;
+                for (; it < 8; it++) {
+                    if (!((ws_refill(b) == SRC_MORE) & (op < omax - 3))) { phase = 1; break; }
+                    u32 const a0 = dstep<FAST>(s1, b, cells), a1 = dstep<FAST>(s2, b, cells);
+                    u32 const a2 = dstep<FAST>(s1, b, cells), a3 = dstep<FAST>(s2, b, cells);
+                    if (al4) *reinterpret_cast<u32*>(out + op) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+                    else { out[op] = (u8)a0; out[op + 1] = (u8)a1; out[op + 2] = (u8)a2; out[op + 3] = (u8)a3; }
+                    op += 4;
+                }
+            } else {                                               // tail (fse_decompress.c:222-235): at most a handful of bytes left
+                for (int it = 0; it < 4; it++) {
+                    if (op > omax - 2) { ret = err(E_DST_TOO_SMALL); phase = 2; break; }
+                    out[op++] = (u8)dstep<FAST>(s1, b, cells);
+                    if (ws_refill(b) == SRC_OVER) { out[op++] = (u8)dstep<FAST>(s2, b, cells); ret = (u64)op; phase = 2; break; }
+                    if (op > omax - 2) { ret = err(E_DST_TOO_SMALL); phase = 2; break; }
+                    out[op++] = (u8)dstep<FAST>(s2, b, cells);
+                    if (ws_refill(b) == SRC_OVER) { out[op++] = (u8)dstep<FAST>(s1, b, cells); ret = (u64)op; phase = 2; break; }
+                }
+            }
+        }
     }
-    return (u64)op;
+    return __shfl_sync(FULL, ret, 0);
 }
 
-// FSE_decompressU16_usingDTable (fseU16.c:273-301), lane 0 only.  cap / return value in symbols.
-__device__ inline u64 lane_decode_u16(u16* out, u64 cap, const u8* cSrc, u64 cSize, const u32* dt)
+// FSE_decompressU16_usingDTable (fseU16.c:273-301).  cap / return value in symbols.
+__device__ inline u64 warp_decode_u16(u16* out, u64 cap, const u8* cSrc, u64 cSize, const u32* dt, u64* win)
 {
+    unsigned const lane = lane_id();
     unsigned const tl = dt[0] & 0xFFFF;
     const u32* const cells = dt + 1;
-    u64 op = 0; GSrc b;
+    u64 op = 0;
     if (cSize < 1) return err(E_CORRUPT);               // the reference dereferences a NULL stream here (documented deviation)
-    gs_open(b, cSrc, cSize);                            // its result is ignored by the reference (:286)
-    u32 st = (u32)gs_read(b, tl); gs_refill(b);
+    WSrc b; b.base = reinterpret_cast<u64>(cSrc); b.len = cSize; b.winBase = 0; b.win = win; b.at = 0; b.w = 0; b.used = 0;
+    u32 st = 0; u64 ret = 0; int phase = 0;             // 0 = stream phase, 1 = drain phase, 2 = done
+    ws_slide(b, cSize >= 8 ? cSize - 8 : 0, win, true);
+    if (lane == 0) { ws_open(b, cSize); st = (u32)ws_read(b, tl); ws_refill(b); }   // open's verdict is ignored by the reference (:286)
 #define FSEB_U16_STEP() do { u32 const cell = cells[st]; out[op++] = (u16)(cell >> 20); \
-                             st = (cell & 0xFFFF) + (u32)gs_read(b, (cell >> 16) & 0xF); } while (0)
-    while (gs_refill(b) < SRC_DONE && op < cap) FSEB_U16_STEP();
-    if (!(b.at == 0 && b.used == 64)) return err(E_CORRUPT);
-    while (st && op < cap) FSEB_U16_STEP();
+                             st = (cell & 0xFFFF) + (u32)ws_read(b, (cell >> 16) & 0xF); } while (0)
+    for (;;) {
+        phase = __shfl_sync(FULL, phase, 0);
+        if (phase == 2) break;
+        u64 const at = __shfl_sync(FULL, b.at, 0);
+        ws_slide(b, at, win, false);
+        if (lane == 0) {
+            if (phase == 0) {
+                int it = 0;
+                for (; it < 24; it++) {                 // <= 24 * 16 bits = 48 bytes per batch
+                    if (!(ws_refill(b) < SRC_DONE && op < cap)) { phase = 1; break; }
+                    FSEB_U16_STEP();
+                }
+            } else {
+                if (!(b.at == 0 && b.used == 64)) { ret = err(E_CORRUPT); phase = 2; }
+                else {
+                    int it = 0;
+                    for (; it < 64 && st && op < cap; it++) FSEB_U16_STEP();
+                    if (!(st && op < cap)) { ret = st ? err(E_CORRUPT) : op; phase = 2; }
+                }
+            }
+        }
+    }
 #undef FSEB_U16_STEP
-    if (st) return err(E_CORRUPT);
-    return op;
+    return __shfl_sync(FULL, ret, 0);
 }
 
 // Builds the DTable image of one block with one warp.  Returns 0 or an error (uniform across the warp).
@@ -272,12 +341,12 @@ fse_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     u64 const e = warp_build_dtable<WIDE>(w, msv, tl);
     if (is_err(e)) { if (lane == 0) results[b] = e; return; }
     __syncwarp();
-    if (lane == 0) {
+    {
         u64 r;
-        if (WIDE) { r = lane_decode_u16(reinterpret_cast<u16*>(out), n / 2, c + h, cs - h, w.dt); if (!is_err(r)) r *= 2; }
-        else if (w.dt[0] >> 16) r = lane_decode_bytes<true>(out, n, c + h, cs - h, w.dt);
-        else r = lane_decode_bytes<false>(out, n, c + h, cs - h, w.dt);
-        results[b] = r;
+        if (WIDE) { r = warp_decode_u16(reinterpret_cast<u16*>(out), n / 2, c + h, cs - h, w.dt, w.win); if (!is_err(r)) r *= 2; }
+        else if (w.dt[0] >> 16) r = warp_decode_bytes<true>(out, n, c + h, cs - h, w.dt, w.win);
+        else r = warp_decode_bytes<false>(out, n, c + h, cs - h, w.dt, w.win);
+        if (lane == 0) results[b] = r;
     }
 }
 
@@ -295,7 +364,8 @@ struct EncWarp {
     u32   start[EncCfg<WIDE>::MSV + 3];
     short norm[EncCfg<WIDE>::MSV + 1];
     u16   cum[EncCfg<WIDE>::MSV + 3];
-    u16   cellSym[EncCfg<WIDE>::CELLS];
+    typename EncCfg<WIDE>::sym_t cellSym[EncCfg<WIDE>::CELLS];
+    u32   cdfs[64], cdnb[64];     // deltaFindState / deltaNbBits of the 64 symbols of the current group (filled by the whole warp)
     u32   slot[64];               // (value | nbBits << 16) of up to 64 consecutive symbols, emission order
     u32   words[32];
 };
@@ -424,7 +494,7 @@ fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, 
         ((u16*)w.ct)[0] = (u16)tl; ((u16*)w.ct)[1] = (u16)msv;
     }
     __syncwarp();
-    warp_spread(w.norm, w.cum, msv, tl, [&](u32 cell, u32 sym) { w.cellSym[cell] = (u16)sym; });
+    warp_spread(w.norm, w.cum, msv, tl, [&](u32 cell, u32 sym) { w.cellSym[cell] = (typename EncCfg<WIDE>::sym_t)sym; });
     __syncwarp();
     {   u16* const next = ((u16*)w.ct) + 2;
         for (u32 u0 = 0; u0 < size; u0 += 32) {                       // next[start[s] + k] = size + u for the k-th cell u of s (:125-128)
@@ -472,15 +542,19 @@ fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, 
     for (u32 hi = n; hi > 0;) {
         u32 const cnt = hi >= 64 ? 64 : hi;
         u32 const lo = hi - cnt;
-        // slot j <-> symbol index hi-1-j
+        // slot j <-> symbol index hi-1-j.  The whole warp first fetches the group's symbols (coalesced) and their
+        // transforms, so that the chain lanes only touch shared memory and their loads do not depend on the state.
+        for (u32 j = lane; j < cnt; j += 32) {
+            u32 const sym = (u32)s[hi - 1 - j];
+            w.cdfs[j] = tt[2 * sym]; w.cdnb[j] = tt[2 * sym + 1];
+        }
+        __syncwarp();
         {
             unsigned const chains = WIDE ? 1u : 2u;
             if (lane < chains) {
-                for (u32 j = 0; j < cnt; j++) {
-                    u32 const idx = hi - 1 - j;
-                    if (!WIDE && (idx & 1) != lane) continue;
-                    u32 const sym = (u32)s[idx];
-                    u32 const dfs = tt[2 * sym], dnb = tt[2 * sym + 1];
+                u32 const j0 = WIDE ? 0u : ((((hi - 1) & 1u) == lane) ? 0u : 1u);      // first slot of this chain in the group
+                for (u32 j = j0; j < cnt; j += chains) {
+                    u32 const dfs = w.cdfs[j], dnb = w.cdnb[j];
                     if (!seeded) {                                   // FSE_initCState2 (fse.h:503-512): no output
                         u32 const nb0 = (dnb + (1u << 15)) >> 16;
                         u32 const v0 = (nb0 << 16) - dnb;

@@ -228,50 +228,60 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
         u32 const seg = (n + 3) / 4;
         int const segBeg = (int)(k * seg);
         int const segEnd = (k < 3) ? (int)((k + 1) * seg) : (int)n;
+        u32 const sTab = (u32)__cvta_generic_to_shared(ctab);
+        u32 const sImg = (u32)__cvta_generic_to_shared(image);
         u64 bitpos = 8ull * (al + P.streamOff[k]);
-        auto fetch = [&](int hi) -> u32 {                           // the 4 symbols below hi-4*lane, highest index in the low byte; 0xFF.. never used when invalid
+        auto fetch = [&](int hi) -> u32 {                           // the 4 symbols below hi-4*lane, highest index in the low byte
             int const top = hi - 4 * (int)lane;                     // exclusive
             u32 v = 0;
             if (top - 4 >= segBeg && ((reinterpret_cast<u64>(s + top) & 3) == 0)) {
-                u32 const x = __ldg(reinterpret_cast<const u32*>(s + top - 4));
-                v = __byte_perm(x, 0, 0x0123);                      // reverse: byte0 = s[top-1]
-            } else {
+                v = __byte_perm(__ldg(reinterpret_cast<const u32*>(s + top - 4)), 0, 0x0123);   // reversed: byte0 = s[top-1]
+            } else if (top > segBeg) {
                 #pragma unroll
                 for (int j = 0; j < 4; j++) { int const i = top - 1 - j; if (i >= segBeg) v |= (u32)s[i] << (8 * j); }
             }
             return v;
         };
-        u32 nxt = (segEnd > segBeg) ? fetch(segEnd) : 0;
-        for (int hi = segEnd; hi > segBeg; hi -= 128) {
-            u32 const cur = nxt;
-            if (hi - 128 > segBeg) nxt = fetch(hi - 128);           // next group's load in flight while this one is packed
-            int const top = hi - 4 * (int)lane;
-            u64 acc = 0; u32 held = 0;
+        auto lds32 = [&](u32 a) -> u32 { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+        auto red_or = [&](u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); };
+        // groups of 128 symbols, walked from the end of the segment; loads run 4 groups ahead of the packing
+        constexpr int PF = 4;
+        u32 pre[PF];
+        #pragma unroll
+        for (int i = 0; i < PF; i++) pre[i] = (segEnd - 128 * i > segBeg) ? fetch(segEnd - 128 * i) : 0u;
+        for (int hi0 = segEnd; hi0 > segBeg; hi0 -= 128 * PF) {
             #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (top - 1 - j >= segBeg) {
-                    u32 const e = ctab[(cur >> (8 * j)) & 0xFF];
-                    acc |= (u64)(e & 0xFFFF) << held;
-                    held += e >> 16;
+            for (int i = 0; i < PF; i++) {
+                int const hi = hi0 - 128 * i;
+                if (hi <= segBeg) break;                            // warp-uniform
+                u32 const cur = pre[i];
+                if (hi - 128 * PF > segBeg) pre[i] = fetch(hi - 128 * PF);
+                int const top = hi - 4 * (int)lane;
+                int const nValid = top - segBeg;                    // symbols available to this lane (>= 4 for all but the last group)
+                u64 acc = 0; u32 held = 0;                          // up to 48 bits
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    u32 const e = lds32(sTab + 4 * ((cur >> (8 * j)) & 0xFF));
+                    if (j < nValid) { acc |= (u64)(e & 0xFFFF) << held; held += e >> 16; }
                 }
-            }
-            u32 incl = held;
-            #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) { u32 const t = __shfl_up_sync(FULL, incl, dd); if (lane >= (unsigned)dd) incl += t; }
-            u32 const sum = __shfl_sync(FULL, incl, 31);
-            if (held) {
-                u64 const at = bitpos + (incl - held);
-                u32* const wp = image + (at >> 5);
-                u32 const sh = (u32)(at & 31);
                 u32 const a0 = (u32)acc, a1 = (u32)(acc >> 32);
-                u32 const w0 = a0 << sh, w1 = __funnelshift_l(a0, a1, sh), w2 = __funnelshift_l(a1, 0, sh);
-                if (w0) atomicOr(wp, w0);
-                if (w1) atomicOr(wp + 1, w1);
-                if (w2) atomicOr(wp + 2, w2);
+                u32 incl = held;
+                #pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { u32 const t = __shfl_up_sync(FULL, incl, dd); if (lane >= (unsigned)dd) incl += t; }
+                u32 const sum = __shfl_sync(FULL, incl, 31);
+                if (held) {
+                    u64 const at = bitpos + (incl - held);
+                    u32 const wa = sImg + 4 * (u32)(at >> 5);
+                    u32 const sh = (u32)(at & 31);
+                    u32 const w0 = a0 << sh, w1 = __funnelshift_l(a0, a1, sh), w2 = __funnelshift_l(a1, 0, sh);
+                    if (w0) red_or(wa, w0);
+                    if (w1) red_or(wa + 4, w1);
+                    if (w2) red_or(wa + 8, w2);
+                }
+                bitpos += sum;
             }
-            bitpos += sum;
         }
-        if (lane == 0) atomicOr(image + (bitpos >> 5), 1u << (bitpos & 31));      // end mark (bitstream.h:256)
+        if (lane == 0) red_or(sImg + 4 * (u32)(bitpos >> 5), 1u << (bitpos & 31));      // end mark (bitstream.h:256)
     }
     __syncthreads();
     // ---- copy out (HBM write) ----
