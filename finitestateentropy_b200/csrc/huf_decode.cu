@@ -20,7 +20,9 @@
 //   * each lane keeps a 64-bit left-aligned bit window in two registers; every two symbols a
 //     predicated block merges the next 32-bit word, taken from a private 16-word shared-memory ring the
 //     lane fills itself with cp.async (global -> shared, no register dependency, waited one visit later);
-//   * output: 8 symbols are packed into one 8-byte store per lane into its quarter of the block;
+//   * output: 16 symbols are packed into one 16-byte store per lane into its quarter of the block.  Global traffic
+//     is inherently per-lane (every lane owns a different stream), so the number of L1 wavefronts -- one per lane per
+//     request -- is what bounds this kernel: 16-byte requests both ways keep it at 1 wavefront per 16 bytes;
 //   * blocks whose long-code region exceeds 192 windows ("hard", e.g. near-flat 256-symbol alphabets),
 //     unaligned segments and ragged tails take a slower per-symbol loop with a canonical-code search;
 //   * the grid is shaped so that every SM gets the same number of blocks per round (a round = 2 CTAs
@@ -43,7 +45,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct __align__(16) Smem {
     u16 main[MAIN_ROWS][G];       // 64 KB   first-level table, column = block
     u16 sub[SUB_ROWS][G];         // 24 KB   long-code windows (index < T); hard blocks park their sorted symbol list here
-    u32 ring[RING][THREADS];      // 16 KB   per-lane stream words (column = thread); table-build scratch before the streams start
+    uint4 ring[RING / 4][THREADS]; // 16 KB   per-lane stream chunks (16 bytes = 4 words, highest address first when consumed); table-build scratch before the streams start
     u16 rankEnd[HUF_MAX_TLOG + 2][G];   // end (exclusive) of weight w's range in tableLog-bit index space
     u16 listStart[HUF_MAX_TLOG + 2][G]; // first position of weight w in the sorted symbol list
     u16 longT[G];                 // number of tableLog-bit windows that start a code longer than 9 bits
@@ -181,7 +183,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     u32 const tl = sm.tlog[col];
 
     u32 fullChunks = 0;                              // chunks 0..fullChunks-1 lie entirely inside the stream (plain 16-byte copies)
-    u32 const ringLo = (u32)__cvta_generic_to_shared(&sm.ring[0][tid]);
+    u32 const ringLo = (u32)__cvta_generic_to_shared(&sm.ring[0][tid]);   // this thread's 16 bytes of chunk slot 0
     // Chunk qq = the aligned 16 bytes ending at chunkTop - 16*qq; it holds stream words 4qq..4qq+3 in descending
     // address order; bytes below the stream start read as 0 (the reference's reader pads the same way).
     auto stage_sync = [&](u32 qq) {                  // boundary / out-of-stream chunks and the initial fill: through registers
@@ -199,19 +201,15 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
                 }
             }
         }
-        u32 const s0 = (4 * qq) & (RING - 1);
-        sm.ring[s0 + 0][tid] = v.w; sm.ring[s0 + 1][tid] = v.z; sm.ring[s0 + 2][tid] = v.y; sm.ring[s0 + 3][tid] = v.x;
+        sm.ring[qq & (RING / 4 - 1)][tid] = v;
     };
-    auto stage_async = [&](u32 qq) {                 // steady state: global -> shared without touching registers (cp.async, 4 x 4 bytes)
+    auto stage_async = [&](u32 qq) {                 // steady state: ONE 16-byte cp.async per chunk (one L1 wavefront), no register dependency
         u64 const top = chunkTop - 16ull * qq;
-        u32 const d0 = ringLo + ((4 * qq) & (RING - 1)) * (THREADS * 4);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\t"
-                     "cp.async.ca.shared.global [%2], [%3], 4;\n\t"
-                     "cp.async.ca.shared.global [%4], [%5], 4;\n\t"
-                     "cp.async.ca.shared.global [%6], [%7], 4;\n\t"
-                     "cp.async.commit_group;"
-                     :: "r"(d0), "l"(top - 4), "r"(d0 + THREADS * 4), "l"(top - 8),
-                        "r"(d0 + 2 * THREADS * 4), "l"(top - 12), "r"(d0 + 3 * THREADS * 4), "l"(top - 16) : "memory");
+        u32 const d0 = ringLo + (qq & (RING / 4 - 1)) * (THREADS * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" :: "r"(d0), "l"(top - 16) : "memory");
+    };
+    auto ring_word = [&](u32 j) -> u32 {             // stream word j (descending addresses): chunk j/4, word 3 - j%4
+        return reinterpret_cast<const u32*>(&sm.ring[(j >> 2) & (RING / 4 - 1)][tid])[3 - (j & 3)];
     };
 
     if (live) {
@@ -264,75 +262,98 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
         stage_sync(0); stage_sync(1); stage_sync(2); stage_sync(3);
         q = 4;
         k = c0 >> 5; r = c0 & 31;
-        u32 const w0 = sm.ring[k & (RING - 1)][tid], w1 = sm.ring[(k + 1) & (RING - 1)][tid];
-        nw = sm.ring[(k + 2) & (RING - 1)][tid];
+        u32 const w0 = ring_word(k), w1 = ring_word(k + 1);
+        nw = ring_word(k + 2);
         hi = __funnelshift_l(w1, w0, r); lo = w1 << r;
     }
 
     // ---- decode ----
     u32 const sMain = (u32)__cvta_generic_to_shared(&sm.main[0][col]);     // + row * 128
     u32 const sSub = (u32)__cvta_generic_to_shared(&sm.sub[0][col]);
-    u32 const ringEnd = ringLo + RING * THREADS * 4;
-    u32 rp = ringLo + ((k + 2) & (RING - 1)) * (THREADS * 4);              // slot `nw` was read from; a refill advances it first
+    u32 const ringBase = (u32)__cvta_generic_to_shared(&sm.ring[0][0]);
+    // ring cursor: byte offset (chunkSlot * 4096 + tid * 16 + word * 4) of the word `nw` was read from; a refill moves it
+    // first: down by 4 inside a chunk, or to word 3 of the next chunk slot.
+    // The word index k = floor(consumed / 32) is not carried through the hot loop: it is recovered from the cursor
+    // and the staging counter q (k + 2 is in [4q-16, 4q-1] because a chunk is staged only when 4q <= k + 14).
+    u32 roff = (((k + 2) >> 2) & (RING / 4 - 1)) * (THREADS * 16) + tid * 16 + (3 - ((k + 2) & 3)) * 4;
     u32 const T = sm.longT[col];
     u32 const shTl = 32 - (tl ? tl : 1);
+    u32 const Thi = T << shTl;                        // window values below this start a code longer than 9 bits (T <= 192 on the fast path)
+    u32 const mulTl = 1u << (tl ? tl : 1);            // (hi * 2^tl) >> 32 == hi >> (32 - tl), computed on the FMA pipe
     bool const hardBlk = sm.hard[col] != 0;
+    auto word_index = [&]() -> u32 {                  // k from the ring cursor
+        u32 const slot = (roff >> 12) * 4 + (3 - ((roff >> 2) & 3));     // == (k + 2) mod 16
+        u32 const lo16 = 4 * q - 16;                  // smallest possible k + 2
+        return lo16 + ((slot - lo16) & (RING - 1)) - 2;
+    };
 
-    // Keep the ring ahead of the consumer.  Called at least every 16 symbols (<= 6 words consumed); a chunk is
-    // staged when its 4 slots are free (4q <= k+15), so afterwards 4q >= k+12: the newest chunk is never needed
-    // before the next call, which is why waiting for all copies but the newest one is enough.
+    // Keep the ring ahead of the consumer.  Called every 8 symbols (<= 3 words consumed in between); at most one chunk
+    // (4 words) is staged per call, when its slots are free (4q <= k+14).  By induction 4q - k >= 13 after every call,
+    // so the words needed before the next call (<= k+5) lie in chunks <= q-3, i.e. in copy groups older than the two
+    // newest ones of this warp: cp.async groups are tracked per WARP (LDGDEPBAR / DEPBAR.LE), one group per call at most.
+    // (Committing two groups in one call and waiting for "all but the newest" exposed a full DRAM latency per call.)
     auto top_up = [&]() {
-        #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            if (4 * q <= k + 15) {
-                if (q < fullChunks) stage_async(q); else stage_sync(q);
-                q++;
-            }
+        u32 const kk = word_index();
+        if (4 * q <= kk + 14) {
+            if (q < fullChunks) stage_async(q); else stage_sync(q);
+            q++;
         }
         if (q >= fullChunks) asm volatile("cp.async.wait_group 0;" ::: "memory");   // tail of the stream: chunks come through registers, nothing may stay pending
-        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 2;" ::: "memory");
     };
-    // one symbol, branch-free: E = nbBits | symbol << 8, window advanced
+    // One symbol, branch-free: E = nbBits | symbol << 8, window advanced.  Integer work is split between the ALU pipe
+    // (and / setp / funnel shifts) and the FMA pipe (mad.hi / mad.lo do the two shifts-and-adds that form the addresses):
+    // both pipes issue one warp instruction every two cycles, and the ALU pipe is what bounds this loop.
 #define HUFD_LOOKUP(E) do { \
-        u32 const i12_ = hi >> shTl; \
-        u32 const aM_ = ((hi >> (32 - MAIN_BITS)) << 7) + sMain; \
-        u32 const aS_ = (i12_ << 7) + sSub; \
-        E = lds_u16(i12_ < T ? aS_ : aM_); \
+        u32 aM_, aS_, i12_, tM_; u16 e16_; \
+        asm volatile("{\n\t.reg .pred p;\n\t" \
+            "and.b32 %3, %5, 0xFF800000;\n\t"            /* top 9 bits */ \
+            "mad.hi.u32 %1, %3, 65536, %6;\n\t"           /* (idx9 << 7) + sMain */ \
+            "setp.lt.u32 p, %5, %8;\n\t" \
+            "mul.hi.u32 %4, %5, %9;\n\t"                   /* top tableLog bits */ \
+            "@p mad.lo.u32 %1, %4, 128, %7;\n\t"          /* (idx << 7) + sSub */ \
+            "ld.shared.u16 %0, [%1];\n\t}" \
+            : "=h"(e16_), "=r"(aM_), "=r"(aS_), "=r"(tM_), "=r"(i12_) \
+            : "r"(hi), "r"(sMain), "r"(sSub), "r"(Thi), "r"(mulTl)); \
+        E = e16_; \
         hi = __funnelshift_l(lo, hi, E); lo = __funnelshift_l(0, lo, E); \
     } while (0)
     // merge the next word when the pair crossed a 32-bit boundary (bit 5 of the running count); all predicated
 #define HUFD_REFILL() asm volatile("{\n\t" \
-        ".reg .pred p, qq;\n\t.reg .b32 t;\n\t" \
+        ".reg .pred p, w0;\n\t.reg .b32 t, u, v;\n\t" \
         "and.b32 t, %4, 32;\n\t" \
         "setp.ne.u32 p, t, 0;\n\t" \
         "and.b32 %4, %4, 31;\n\t" \
         "shf.l.wrap.b32 t, %2, 0, %4;\n\t" \
         "@p or.b32 %0, %0, t;\n\t" \
         "@p shl.b32 %1, %2, %4;\n\t" \
-        "@p add.u32 %5, %5, 1;\n\t" \
-        "@p add.u32 %3, %3, %6;\n\t" \
-        "setp.ge.and.u32 qq, %3, %7, p;\n\t" \
-        "@qq sub.u32 %3, %3, %8;\n\t" \
-        "@p ld.shared.u32 %2, [%3];\n\t" \
-        "}" : "+r"(hi), "+r"(lo), "+r"(nw), "+r"(rp), "+r"(r), "+r"(k) : "n"(THREADS * 4), "r"(ringEnd), "n"(RING * THREADS * 4) : "memory")
+        "and.b32 u, %3, 12;\n\t" \
+        "setp.eq.u32 w0, u, 0;\n\t"                      /* last word of the chunk consumed: jump to word 3 of the next slot */ \
+        "add.u32 v, %3, -4;\n\t" \
+        "mad.lo.u32 u, %5, 1, %3;\n\t" \
+        "@w0 and.b32 v, u, %6;\n\t" \
+        "@p mov.b32 %3, v;\n\t" \
+        "@p add.u32 u, v, %7;\n\t" \
+        "@p ld.shared.u32 %2, [u];\n\t" \
+        "}" : "+r"(hi), "+r"(lo), "+r"(nw), "+r"(roff), "+r"(r) : "r"(THREADS * 16 + 12), "n"(RING * THREADS * 4 - 1), "r"(ringBase) : "memory")
 
     u32 pos = 0;
-    bool const fastOk = go && !hardBlk && ((reinterpret_cast<u64>(outp) & 7) == 0);
+    bool const fastOk = go && !hardBlk && ((reinterpret_cast<u64>(outp) & 15) == 0);
     if (fastOk) {
-        u32 const nIter = segLen >> 3;
-        for (u32 it = 0; it < nIter; it++) {
-            if ((it & 1) == 0) top_up();
-            u32 o0, o1, e0, e1;
-            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
-            o0 = __byte_perm(e0, e1, 0x0051);                       // {sym0, sym1, x, x}
-            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
-            o0 = __byte_perm(o0, __byte_perm(e0, e1, 0x0051), 0x5410);
-            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
-            o1 = __byte_perm(e0, e1, 0x0051);
-            HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
-            o1 = __byte_perm(o1, __byte_perm(e0, e1, 0x0051), 0x5410);
-            *reinterpret_cast<uint2*>(outp + pos) = make_uint2(o0, o1);
-            pos += 8;
+        u32 const nIter = segLen >> 4;
+        for (u32 it = 0; it < nIter; it++) {             // 16 symbols -> one 16-byte store per lane
+            u32 o[4], e0, e1;
+            #pragma unroll
+            for (int h = 0; h < 4; h++) {
+                if ((h & 1) == 0) top_up();              // every 8 symbols
+                u32 t;
+                HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
+                t = __byte_perm(e0, e1, 0x0051);                        // {sym0, sym1, x, x}
+                HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
+                o[h] = __byte_perm(t, __byte_perm(e0, e1, 0x0051), 0x5410);
+            }
+            *reinterpret_cast<uint4*>(outp + pos) = make_uint4(o[0], o[1], o[2], o[3]);
+            pos += 16;
         }
     }
     // ragged tails, unaligned segments and hard blocks: one symbol at a time
@@ -358,7 +379,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     asm volatile("cp.async.wait_all;" ::: "memory");
     // ---- verdict: every stream must be consumed exactly (huf_decompress.c:348-349) ----
     if (go) {
-        u64 const consumed = 32ull * k + (r & 31);
+        u64 const consumed = 32ull * word_index() + (r & 31);
         u64 const expect = 8ull * (chunkTop - sBegin);
         if (consumed != expect) atomicMin(&sm.status[col], (u32)(5u << 8 | E_CORRUPT));
     }

@@ -69,20 +69,18 @@ __device__ __forceinline__ void warp_hist_range(u32* cnt, const u8* s, u32 begin
         i = head;
         u32 const nvec = (end - i) / 16;
         const uint4* const gv = reinterpret_cast<const uint4*>(s + i);
-        for (u32 v0 = 0; v0 < nvec; v0 += 64) {                    // two loads in flight per lane
-            u32 const va = v0 + lane, vb = v0 + 32 + lane;
-            uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
-            if (va < nvec) xa = __ldg(gv + va);
-            if (vb < nvec) xb = __ldg(gv + vb);
+        for (u32 v0 = 0; v0 < nvec; v0 += 128) {                   // four 16-byte loads in flight per lane before the first use
+            uint4 x[4];
             #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if ((h == 0 ? va : vb) >= nvec) continue;
-                uint4 const v = h == 0 ? xa : xb;
-                u32 const wd[4] = { v.x, v.y, v.z, v.w };
+            for (int h = 0; h < 4; h++) { u32 const vi = v0 + 32 * h + lane; x[h] = (vi < nvec) ? __ldg(gv + vi) : make_uint4(0, 0, 0, 0); }
+            #pragma unroll
+            for (int h = 0; h < 4; h++) {
+                if (v0 + 32 * h + lane >= nvec) continue;
+                u32 const wd[4] = { x[h].x, x[h].y, x[h].z, x[h].w };
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    u32 const x = wd[k];
-                    u32 const b0 = x & 0xFF, b1 = (x >> 8) & 0xFF, b2 = (x >> 16) & 0xFF, b3 = x >> 24;
+                    u32 const y = wd[k];
+                    u32 const b0 = y & 0xFF, b1 = (y >> 8) & 0xFF, b2 = (y >> 16) & 0xFF, b3 = y >> 24;
                     if ((b0 == b1) & (b1 == b2) & (b2 == b3)) atomicAdd(&cnt[b0], 4u);
                     else { atomicAdd(&cnt[b0], 1u); atomicAdd(&cnt[b1], 1u); atomicAdd(&cnt[b2], 1u); atomicAdd(&cnt[b3], 1u); }
                 }
@@ -231,14 +229,15 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
         u32 const sTab = (u32)__cvta_generic_to_shared(ctab);
         u32 const sImg = (u32)__cvta_generic_to_shared(image);
         u64 bitpos = 8ull * (al + P.streamOff[k]);
-        auto fetch = [&](int hi) -> u32 {                           // the 4 symbols below hi-4*lane, highest index in the low byte
+        // the 4 symbols below hi-4*lane as one little-endian word (byte 3 = highest index = emitted first).  The raw
+        // word is kept as loaded: warps issue in order, so touching it here would stall on the load right away.
+        auto fetch = [&](int hi) -> u32 {
             int const top = hi - 4 * (int)lane;                     // exclusive
             u32 v = 0;
-            if (top - 4 >= segBeg && ((reinterpret_cast<u64>(s + top) & 3) == 0)) {
-                v = __byte_perm(__ldg(reinterpret_cast<const u32*>(s + top - 4)), 0, 0x0123);   // reversed: byte0 = s[top-1]
-            } else if (top > segBeg) {
+            if (top - 4 >= segBeg && ((reinterpret_cast<u64>(s + top) & 3) == 0)) v = __ldg(reinterpret_cast<const u32*>(s + top - 4));
+            else if (top > segBeg) {
                 #pragma unroll
-                for (int j = 0; j < 4; j++) { int const i = top - 1 - j; if (i >= segBeg) v |= (u32)s[i] << (8 * j); }
+                for (int j = 0; j < 4; j++) { int const i = top - 1 - j; if (i >= segBeg) v |= (u32)s[i] << (8 * (3 - j)); }
             }
             return v;
         };
@@ -261,7 +260,7 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                 u64 acc = 0; u32 held = 0;                          // up to 48 bits
                 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    u32 const e = lds32(sTab + 4 * ((cur >> (8 * j)) & 0xFF));
+                    u32 const e = lds32(sTab + 4 * ((cur >> (8 * (3 - j))) & 0xFF));
                     if (j < nValid) { acc |= (u64)(e & 0xFFFF) << held; held += e >> 16; }
                 }
                 u32 const a0 = (u32)acc, a1 = (u32)(acc >> 32);
