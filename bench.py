@@ -40,7 +40,7 @@ CODEC_ID = {"fse": 0, "huf": 1, "u16": 2}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mib", type=int, default=1024, help="uncompressed MiB per GPU (BASELINE config: 1024)")
@@ -122,37 +122,47 @@ def cpu_probagen(n, p):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)"""
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line): one streaming
+    `nvidia-smi -lms 20` process, every row time-stamped on arrival; summary() keeps the rows that fall inside
+    [t0, t1] (the timed region) plus the closest neighbours when the region is shorter than the sampling period."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows = []; self.stop = False; self.index = index
+        self.rows = []; self.proc = None; self.index = index
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
-            try:
-                o = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                            timeout=5).decode().strip()
-                self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.strip().split(",")]))
+        except Exception:
+            pass
 
-    def __enter__(self):
-        self.t.start(); return self
+    def start(self):
+        self.t.start()
+        time.sleep(0.15)                                           # let the first rows arrive before the timed region opens
 
-    def __exit__(self, *a):
-        self.stop = True; self.t.join(timeout=6)
+    def stop(self):
+        time.sleep(0.05)
+        if self.proc is not None:
+            self.proc.terminate()
+        self.t.join(timeout=3)
 
-    def summary(self):
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+    def summary(self, t0, t1):
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1]
+        if len(inside) < 3:                                        # very short region: take the nearest rows around it
+            near = sorted(self.rows, key=lambda tr: abs(tr[0] - (t0 + t1) / 2))[:5]
+            inside = [r for (_, r) in near]
+        sm = sorted(int(float(r[0])) for r in inside if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in inside if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in inside if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in inside if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "samples": len(inside), "samples_total": len(self.rows)}
 
 
 def measured_peak():
@@ -273,9 +283,10 @@ def run_b200(a):
     # ---- timed region: K steps, events on the launching (torch current) stream ----
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
     if sampler:
-        sampler.__enter__()
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(a.steps):
@@ -284,8 +295,9 @@ def run_b200(a):
         ev[i][2].record()
     t1.record()
     barrier()
+    wall1 = time.perf_counter()
     if sampler:
-        sampler.__exit__()
+        sampler.stop()
     total_ms = t0.elapsed_time(t1)
     enc_ms = sum(ev[i][0].elapsed_time(ev[i][1]) for i in range(a.steps)) / a.steps
     dec_ms = sum(ev[i][1].elapsed_time(ev[i][2]) for i in range(a.steps)) / a.steps
@@ -334,7 +346,7 @@ def run_b200(a):
     # ---- roofline of the dominant kernel (algorithmic bytes: S + C each way) ----
     peak, peak_src = measured_peak()
     alg = n + csum
-    kern = {"huf_encode_kernel" if a.codec == "huf" else "fse_encode_kernel": enc_ms, "huf_decode_kernel" if a.codec == "huf" else "fse_decode_kernel": dec_ms}
+    kern = {"huf_plan_kernel+huf_emit_kernel" if a.codec == "huf" else "fse_encode_kernel": enc_ms, "huf_decode_kernel" if a.codec == "huf" else "fse_decode_kernel": dec_ms}
     dom = max(kern, key=kern.get)
     roof = lambda ms: round(alg / (ms * 1e-3) / 1e9, 2)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": roof(kern[dom]), "peak": peak, "unit": "GB/s",
@@ -371,8 +383,8 @@ def run_b200(a):
             "encode_gbs_per_gpu": round(n / (enc_ms * 1e-3) / 1e9, 2), "decode_gbs_per_gpu": round(n / (dec_ms * 1e-3) / 1e9, 2),
             "per_gpu": round(value / world, 3), "compressed_ratio": round(csum / n, 5),
             "bit_exact": bit_exact, "roundtrip_ok": ok_rt,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * a.steps,
-            "clocks": sampler.summary() if sampler else None}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (3 if a.codec == "huf" else 2) * a.steps,
+            "clocks": sampler.summary(wall0, wall1) if sampler else None}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

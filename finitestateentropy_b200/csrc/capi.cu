@@ -428,6 +428,7 @@ FSEB_API size_t FSEB200_probagen(void* dDst, size_t nBytes, size_t streamOffset,
     unsigned char table[4096];
     int remaining = 4096; unsigned pos = 0, sym = 0;
     if (p == 0.0) p = 0.005;
+    if (!(p > 0.0 && p <= 1.0)) return err(E_GENERIC);                  // a probability, not a percentage (the reference's CLI divides by 100)
     while (remaining) {
         unsigned n = (unsigned)(remaining * p);
         if (!n) n = 1;
@@ -448,8 +449,10 @@ FSEB_API size_t FSEB200_genU16(void* dDst, size_t nSymbols, size_t streamOffset,
 {
     unsigned short table[4096];
     unsigned remaining = 4096, pos = 0; unsigned short v = (unsigned short)start;
+    if (!(p >= 0.0 && p <= 1.0)) return err(E_GENERIC);
     while (remaining) {
-        unsigned const n = (unsigned)(remaining * p) + 1;
+        unsigned n = (unsigned)(remaining * p) + 1;
+        if (n > remaining) n = remaining;
         unsigned const end = pos + n;
         while (pos < end) table[pos++] = v;
         v++; if (v >= U16_MAX_SV) v = 1;
@@ -500,17 +503,35 @@ FSEB_API size_t FSEB200_compress_host(int codec, void* hCBuf, size_t slot, size_
     std::lock_guard<std::mutex> lock(P.mu);
     size_t const nb = (srcTotal + blockSize - 1) / blockSize;
     P.ensure(CHUNK_BLOCKS * blockSize, CHUNK_BLOCKS * slot, CHUNK_BLOCKS);
-    int k = 0;
-    for (size_t b0 = 0; b0 < nb; b0 += CHUNK_BLOCKS, k = (k + 1) % HostPipe::NS) {
-        size_t const cb = nb - b0 < CHUNK_BLOCKS ? nb - b0 : CHUNK_BLOCKS;
+    size_t const nChunks = (nb + CHUNK_BLOCKS - 1) / CHUNK_BLOCKS;
+    // Software pipeline over chunks: chunk i+1 is queued (H2D + kernels + sizes D2H) before chunk i is finished.
+    // Finishing = wait for its sizes, then copy back only the used width of its slots (strided 2-D copy): the
+    // compressed side of the PCIe traffic shrinks from `slot` to max(cSize) bytes per block.
+    auto queue = [&](size_t ci) {
+        int const k = (int)(ci % HostPipe::NS);
+        size_t const b0 = ci * CHUNK_BLOCKS, cb = nb - b0 < CHUNK_BLOCKS ? nb - b0 : CHUNK_BLOCKS;
         size_t const off = b0 * blockSize;
         size_t const bytes = (off + cb * blockSize <= srcTotal) ? cb * blockSize : srcTotal - off;
         cudaStream_t s = P.st[k];
         CK(cudaMemcpyAsync(P.dA[k], (const unsigned char*)hSrc + off, bytes, cudaMemcpyHostToDevice, s));
         CK(fn(geom(bytes, blockSize, slot), P.dB[k], P.dS[k], P.dA[k], maxSymbolValue, tableLog, s));
-        CK(cudaMemcpyAsync((unsigned char*)hCBuf + b0 * slot, P.dB[k], cb * slot, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(hCSizes + b0, P.dS[k], cb * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    };
+    auto finish = [&](size_t ci) {
+        int const k = (int)(ci % HostPipe::NS);
+        size_t const b0 = ci * CHUNK_BLOCKS, cb = nb - b0 < CHUNK_BLOCKS ? nb - b0 : CHUNK_BLOCKS;
+        cudaStream_t s = P.st[k];
+        CK(cudaStreamSynchronize(s));
+        size_t width = 0;
+        for (size_t b = 0; b < cb; b++) { size_t const c = hCSizes[b0 + b]; if (!is_err(c) && c > width) width = c; }
+        width = (width + 63) & ~(size_t)63; if (width > slot) width = slot;
+        if (width) CK(cudaMemcpy2DAsync((unsigned char*)hCBuf + b0 * slot, slot, P.dB[k], slot, width, cb, cudaMemcpyDeviceToHost, s));
+    };
+    for (size_t ci = 0; ci < nChunks; ci++) {
+        if (ci >= (size_t)HostPipe::NS - 1) finish(ci - (HostPipe::NS - 1));     // frees the buffers chunk ci+... will reuse next
+        queue(ci);
     }
+    for (size_t ci = (nChunks >= (size_t)HostPipe::NS - 1 ? nChunks - (HostPipe::NS - 1) : 0); ci < nChunks; ci++) finish(ci);
     for (int i = 0; i < HostPipe::NS; i++) CK(cudaStreamSynchronize(P.st[i]));
     return 0;
 }
@@ -531,7 +552,10 @@ FSEB_API size_t FSEB200_decompress_host(int codec, void* hDst, size_t dstTotal, 
         size_t const off = b0 * blockSize;
         size_t const bytes = (off + cb * blockSize <= dstTotal) ? cb * blockSize : dstTotal - off;
         cudaStream_t s = P.st[k];
-        CK(cudaMemcpyAsync(P.dB[k], (const unsigned char*)hCBuf + b0 * slot, cb * slot, cudaMemcpyHostToDevice, s));
+        size_t width = 0;
+        for (size_t bb = 0; bb < cb; bb++) { size_t const c = hCSizes[b0 + bb]; if (!is_err(c) && c > width) width = c; }
+        width = (width + 16 + 63) & ~(size_t)63; if (width > slot) width = slot;     // +16: kernels read whole aligned 16-byte chunks
+        if (width) CK(cudaMemcpy2DAsync(P.dB[k], slot, (const unsigned char*)hCBuf + b0 * slot, slot, width, cb, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(P.dS[k], hCSizes + b0, cb * sizeof(u64), cudaMemcpyHostToDevice, s));
         CK(fn(geom(bytes, blockSize, slot), P.dA[k], P.dB[k], P.dS[k], P.dS[k] + CHUNK_BLOCKS, nullptr, s));
         CK(cudaMemcpyAsync((unsigned char*)hDst + off, P.dA[k], bytes, cudaMemcpyDeviceToHost, s));

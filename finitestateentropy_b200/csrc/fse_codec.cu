@@ -156,63 +156,137 @@ __device__ __forceinline__ int ws_refill(WSrc& b)                  // bitstream.
     return st;
 }
 
-template <bool FAST>
-__device__ __forceinline__ u32 dstep(u32& state, WSrc& b, const u32* cells)
+// ---- fast chain reader -------------------------------------------------------------------------
+// The reference's reader is byte-granular: (ptr, bitsConsumed) and a 64-bit container re-read at every reload.
+// Its loop control depends only on those two counters, never on the container's value, and bits that lie outside
+// the stream can only flow into a state that is never looked up again (after such a read the very next reload
+// reports overflow and the loop emits one symbol of the OTHER state and stops).  So the chain below keeps
+//   * the two counters, updated exactly as BIT_reloadDStream does (cheap integer ops off the critical path), and
+//   * the actual bits in a 64-bit left-aligned register window fed with aligned 32-bit words from the staged
+//     shared-memory window (like the Huff0 decoder), so that a symbol costs LDS + 3 dependent ALU ops.
+struct Chain {
+    u32 hi, lo, vb;                 // window and number of valid bits in it
+    u32 noff;                       // byte offset in the staged window of the next (lower) 32-bit word
+    u64 at; u32 used;               // the reference's ptr - start and bitsConsumed
+};
+__device__ __forceinline__ void ch_fill(Chain& c, const u32* win32)
 {
-    u32 const cell = cells[state];
-    u32 const nb = cell >> 24;
-    u32 const low = (u32)(FAST ? ws_read_fast(b, nb) : ws_read(b, nb));
-    state = (cell & 0xFFFF) + low;
-    return (cell >> 16) & 0xFF;
+    while (c.vb <= 32) {
+        u32 const w = c.noff < WIN ? win32[c.noff >> 2] : 0u; c.noff -= 4;   // below the staged envelope only when the stream is exhausted
+        u64 W = ((u64)c.hi << 32) | c.lo;
+        W |= (u64)w << (32 - c.vb);
+        c.hi = (u32)(W >> 32); c.lo = (u32)W; c.vb += 32;
+    }
+}
+__device__ __forceinline__ u32 ch_take(Chain& c, u32 nb)            // nb <= 16, window holds >= nb valid bits
+{
+    u32 const v = __funnelshift_l(c.hi, 0, nb);                     // top nb bits (0 for nb == 0)
+    c.hi = __funnelshift_l(c.lo, c.hi, nb); c.lo = c.lo << nb;
+    c.vb -= nb; c.used += nb;
+    return v;
+}
+__device__ __forceinline__ int ch_reload(Chain& c)                  // BIT_reloadDStream on the counters (bitstream.h:416-440)
+{
+    if (c.used > 64) return SRC_OVER;
+    if (c.at >= 8) { c.at -= c.used >> 3; c.used &= 7; return SRC_MORE; }
+    if (c.at == 0) return c.used < 64 ? SRC_ENDBUF : SRC_DONE;
+    u64 nb = c.used >> 3; int st = SRC_MORE;
+    if (c.at < nb) { nb = c.at; st = SRC_ENDBUF; }
+    c.at -= nb; c.used -= (u32)nb * 8;
+    return st;
+}
+// warp-wide window maintenance for the chain: keeps >= 64 staged bytes below the next word
+__device__ __forceinline__ void ch_slide(WSrc& b, Chain& c, u64* win)
+{
+    u32 const noff = __shfl_sync(FULL, c.noff, 0);
+    u64 const lowest = b.base & ~15ull;
+    if (noff >= 64 || b.winBase <= lowest) return;
+    u64 const nextA = b.winBase + noff;                             // absolute address of the next word
+    u64 nb = ((nextA + 4 + 15) & ~15ull) - WIN;
+    if (nb < lowest || nb > nextA) nb = lowest;
+    u64 const endAddr = (b.base + b.len + 15) & ~15ull;
+    unsigned const lane = lane_id();
+    u64 const a = nb + 16ull * lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (a < endAddr) v = __ldg(reinterpret_cast<const uint4*>(a));
+    __syncwarp();
+    reinterpret_cast<uint4*>(win)[lane] = v;
+    c.noff = (u32)(nextA - nb);
+    b.winBase = nb;
+    __syncwarp();
+}
+// opens the stream on lane 0: end-mark checks of BIT_initDStream (bitstream.h:272-318), counters, first bits
+__device__ inline u64 ch_open(Chain& c, const WSrc& b, const u32* win32)
+{
+    u64 const len = b.len;
+    c.hi = c.lo = c.vb = 0; c.at = 0; c.used = 0;
+    if (len < 1) return err(E_SRC_WRONG);
+    u64 const e = b.base + len;                                     // one past the last byte
+    u64 const top4 = (e + 3) & ~3ull;
+    c.noff = (u32)(top4 - 4 - b.winBase);
+    u32 const lastWord = win32[c.noff >> 2];
+    u32 const last = (lastWord >> (8 * (u32)((e - 1) & 3))) & 0xFF;
+    if (last == 0) return err(len >= 8 ? E_GENERIC : E_CORRUPT);
+    u32 const skip = (u32)(8 * (top4 - e)) + (8 - hibit(last));    // garbage above the stream + zero padding + end mark
+    ch_fill(c, win32);
+    (void)ch_take(c, skip > 16 ? 16 : skip); if (skip > 16) (void)ch_take(c, skip - 16);
+    ch_fill(c, win32);
+    if (len >= 8) { c.at = len - 8; c.used = 8 - hibit(last); }
+    else { c.at = 0; c.used = 8 - hibit(last) + (u32)(8 - len) * 8; }
+    return len;
 }
 
-// FSE_decompress_usingDTable_generic (fse_decompress.c:178-238).  The chain runs on lane 0 in batches of
-// up to 8 loop iterations (<= 48 stream bytes); between batches the warp slides the window.  Returns on all lanes.
-template <bool FAST>
+#define FSEB_DSTEP(ST, OUT) do { u32 const cell_ = cells[ST]; u32 const low_ = ch_take(c, cell_ >> 24); \
+                                 OUT = (cell_ >> 16) & 0xFF; ST = (cell_ & 0xFFFF) + low_; } while (0)
+
+// FSE_decompress_usingDTable_generic (fse_decompress.c:178-238).  The chain runs on lane 0 in batches of up to 8 loop
+// iterations (<= 48 stream bytes); between batches the warp slides the staged window.  Returns on all lanes.
 __device__ inline u64 warp_decode_bytes(u8* out, u64 cap, const u8* cSrc, u64 cSize, const u32* dt, u64* win)
 {
     unsigned const lane = lane_id();
     unsigned const tl = dt[0] & 0xFFFF;
     const u32* const cells = dt + 1;
+    const u32* const win32 = reinterpret_cast<const u32*>(win);
     long long const omax = (long long)cap;
     long long op = 0;
     WSrc b; b.base = reinterpret_cast<u64>(cSrc); b.len = cSize; b.winBase = 0; b.win = win; b.at = 0; b.w = 0; b.used = 0;
+    Chain c; c.hi = c.lo = c.vb = 0; c.noff = 0; c.at = 0; c.used = 0;
     u32 s1 = 0, s2 = 0;
     u64 ret = 0; int phase = 0;                                    // 0 = main loop, 1 = tail, 2 = finished
     ws_slide(b, cSize >= 8 ? cSize - 8 : 0, win, true);
     if (lane == 0) {
-        u64 const e = ws_open(b, cSize);
+        u64 const e = ch_open(c, b, win32);
         if (is_err(e)) { ret = e; phase = 2; }
         else {
-            s1 = (u32)ws_read(b, tl); ws_refill(b);
-            s2 = (u32)ws_read(b, tl); ws_refill(b);
+            s1 = ch_take(c, tl); ch_reload(c); ch_fill(c, win32);
+            s2 = ch_take(c, tl); ch_reload(c); ch_fill(c, win32);
         }
     }
     bool const al4 = (reinterpret_cast<u64>(out) & 3) == 0;
     for (;;) {
         phase = __shfl_sync(FULL, phase, 0);
         if (phase == 2) break;
-        u64 const at = __shfl_sync(FULL, b.at, 0);
-        ws_slide(b, at, win, false);
+        ch_slide(b, c, win);
         if (lane == 0) {
             if (phase == 0) {
-                int it = 0;
-                for (; it < 8; it++) {
-                    if (!((ws_refill(b) == SRC_MORE) & (op < omax - 3))) { phase = 1; break; }
-                    u32 const a0 = dstep<FAST>(s1, b, cells), a1 = dstep<FAST>(s2, b, cells);
-                    u32 const a2 = dstep<FAST>(s1, b, cells), a3 = dstep<FAST>(s2, b, cells);
+                for (int it = 0; it < 8; it++) {
+                    if (!((ch_reload(c) == SRC_MORE) & (op < omax - 3))) { phase = 1; break; }
+                    u32 a0, a1, a2, a3;
+                    FSEB_DSTEP(s1, a0); FSEB_DSTEP(s2, a1); ch_fill(c, win32);      // <= 24 bits per pair, >= 33 valid after a fill
+                    FSEB_DSTEP(s1, a2); FSEB_DSTEP(s2, a3); ch_fill(c, win32);
                     if (al4) *reinterpret_cast<u32*>(out + op) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
                     else { out[op] = (u8)a0; out[op + 1] = (u8)a1; out[op + 2] = (u8)a2; out[op + 3] = (u8)a3; }
                     op += 4;
                 }
-            } else {                                               // tail (fse_decompress.c:222-235): at most a handful of bytes left
+            } else {                                               // tail (fse_decompress.c:222-235): a handful of symbols
                 for (int it = 0; it < 4; it++) {
+                    u32 sy;
                     if (op > omax - 2) { ret = err(E_DST_TOO_SMALL); phase = 2; break; }
-                    out[op++] = (u8)dstep<FAST>(s1, b, cells);
-                    if (ws_refill(b) == SRC_OVER) { out[op++] = (u8)dstep<FAST>(s2, b, cells); ret = (u64)op; phase = 2; break; }
+                    FSEB_DSTEP(s1, sy); out[op++] = (u8)sy; ch_fill(c, win32);
+                    if (ch_reload(c) == SRC_OVER) { FSEB_DSTEP(s2, sy); out[op++] = (u8)sy; ret = (u64)op; phase = 2; break; }
                     if (op > omax - 2) { ret = err(E_DST_TOO_SMALL); phase = 2; break; }
-                    out[op++] = (u8)dstep<FAST>(s2, b, cells);
-                    if (ws_refill(b) == SRC_OVER) { out[op++] = (u8)dstep<FAST>(s1, b, cells); ret = (u64)op; phase = 2; break; }
+                    FSEB_DSTEP(s2, sy); out[op++] = (u8)sy; ch_fill(c, win32);
+                    if (ch_reload(c) == SRC_OVER) { FSEB_DSTEP(s1, sy); out[op++] = (u8)sy; ret = (u64)op; phase = 2; break; }
                 }
             }
         }
@@ -226,28 +300,45 @@ __device__ inline u64 warp_decode_u16(u16* out, u64 cap, const u8* cSrc, u64 cSi
     unsigned const lane = lane_id();
     unsigned const tl = dt[0] & 0xFFFF;
     const u32* const cells = dt + 1;
+    const u32* const win32 = reinterpret_cast<const u32*>(win);
     u64 op = 0;
     if (cSize < 1) return err(E_CORRUPT);               // the reference dereferences a NULL stream here (documented deviation)
     WSrc b; b.base = reinterpret_cast<u64>(cSrc); b.len = cSize; b.winBase = 0; b.win = win; b.at = 0; b.w = 0; b.used = 0;
+    Chain c; c.hi = c.lo = c.vb = 0; c.noff = 0; c.at = 0; c.used = 0;
     u32 st = 0; u64 ret = 0; int phase = 0;             // 0 = stream phase, 1 = drain phase, 2 = done
     ws_slide(b, cSize >= 8 ? cSize - 8 : 0, win, true);
-    if (lane == 0) { ws_open(b, cSize); st = (u32)ws_read(b, tl); ws_refill(b); }   // open's verdict is ignored by the reference (:286)
+    if (lane == 0) {
+        u64 const e = ch_open(c, b, win32);             // the reference ignores the verdict (:286) and goes on with bitsConsumed = 0 (+ padding)
+        if (is_err(e)) {                                // missing end mark: nothing is skipped, the stream is read from its last bit
+            u64 const endA = b.base + cSize, top4 = (endA + 3) & ~3ull;
+            c.hi = c.lo = c.vb = 0; c.noff = (u32)(top4 - 4 - b.winBase);
+            ch_fill(c, win32);
+            u32 const skip = (u32)(8 * (top4 - endA));
+            (void)ch_take(c, skip > 16 ? 16 : skip); if (skip > 16) (void)ch_take(c, skip - 16);
+            ch_fill(c, win32);
+            c.used = 0;                                 // bitstream.h:283 / :304: bitsConsumed stays 0 when the last byte is 0
+            c.at = cSize >= 8 ? cSize - 8 : 0;
+            if (cSize < 8) {                            // short container: the stream sits in its low bytes under (8 - len) zero bytes
+                u64 W = ((u64)c.hi << 32) | c.lo; W >>= (8 - cSize) * 8;
+                c.hi = (u32)(W >> 32); c.lo = (u32)W; c.vb = 64;
+            }
+        }
+        st = ch_take(c, tl); ch_reload(c); ch_fill(c, win32);
+    }
 #define FSEB_U16_STEP() do { u32 const cell = cells[st]; out[op++] = (u16)(cell >> 20); \
-                             st = (cell & 0xFFFF) + (u32)ws_read(b, (cell >> 16) & 0xF); } while (0)
+                             st = (cell & 0xFFFF) + ch_take(c, (cell >> 16) & 0xF); ch_fill(c, win32); } while (0)
     for (;;) {
         phase = __shfl_sync(FULL, phase, 0);
         if (phase == 2) break;
-        u64 const at = __shfl_sync(FULL, b.at, 0);
-        ws_slide(b, at, win, false);
+        ch_slide(b, c, win);
         if (lane == 0) {
             if (phase == 0) {
-                int it = 0;
-                for (; it < 24; it++) {                 // <= 24 * 16 bits = 48 bytes per batch
-                    if (!(ws_refill(b) < SRC_DONE && op < cap)) { phase = 1; break; }
+                for (int it = 0; it < 24; it++) {       // <= 24 * 16 bits = 48 bytes per batch
+                    if (!(ch_reload(c) < SRC_DONE && op < cap)) { phase = 1; break; }
                     FSEB_U16_STEP();
                 }
             } else {
-                if (!(b.at == 0 && b.used == 64)) { ret = err(E_CORRUPT); phase = 2; }
+                if (!(c.at == 0 && c.used == 64)) { ret = err(E_CORRUPT); phase = 2; }
                 else {
                     int it = 0;
                     for (; it < 64 && st && op < cap; it++) FSEB_U16_STEP();
@@ -259,6 +350,7 @@ __device__ inline u64 warp_decode_u16(u16* out, u64 cap, const u8* cSrc, u64 cSi
 #undef FSEB_U16_STEP
     return __shfl_sync(FULL, ret, 0);
 }
+#undef FSEB_DSTEP
 
 // Builds the DTable image of one block with one warp.  Returns 0 or an error (uniform across the warp).
 template <bool WIDE>
@@ -344,8 +436,7 @@ fse_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     {
         u64 r;
         if (WIDE) { r = warp_decode_u16(reinterpret_cast<u16*>(out), n / 2, c + h, cs - h, w.dt, w.win); if (!is_err(r)) r *= 2; }
-        else if (w.dt[0] >> 16) r = warp_decode_bytes<true>(out, n, c + h, cs - h, w.dt, w.win);
-        else r = warp_decode_bytes<false>(out, n, c + h, cs - h, w.dt, w.win);
+        else r = warp_decode_bytes(out, n, c + h, cs - h, w.dt, w.win);
         if (lane == 0) results[b] = r;
     }
 }

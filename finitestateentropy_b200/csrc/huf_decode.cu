@@ -287,19 +287,28 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
         return lo16 + ((slot - lo16) & (RING - 1)) - 2;
     };
 
-    // Keep the ring ahead of the consumer.  Called every 8 symbols (<= 3 words consumed in between); at most one chunk
-    // (4 words) is staged per call, when its slots are free (4q <= k+14).  By induction 4q - k >= 13 after every call,
-    // so the words needed before the next call (<= k+5) lie in chunks <= q-3, i.e. in copy groups older than the two
-    // newest ones of this warp: cp.async groups are tracked per WARP (LDGDEPBAR / DEPBAR.LE), one group per call at most.
-    // (Committing two groups in one call and waiting for "all but the newest" exposed a full DRAM latency per call.)
+    // Keep the ring ahead of the consumer.  Called every 16 symbols (<= 6 words consumed in between).  Normal case: one
+    // chunk (4 words) is staged asynchronously when its slots are free (4q <= k+14).  If that leaves less than the
+    // worst case of the next interval in the ring (4q - k < 13; only for data averaging > 8 bits/symbol), more chunks
+    // are staged through registers and every pending copy is awaited.  Otherwise the words needed before the next call
+    // (<= k+8 < 4q-4) are older than the newest copy group of this warp -- cp.async groups are tracked per WARP
+    // (LDGDEPBAR / DEPBAR.LE), at most one group per call -- so waiting for all but the newest is enough.
+    // (Committing two groups per call and waiting for "all but the newest" exposed a DRAM latency per call.)
+    u64 gsrc = chunkTop - 16ull * (q + 1);            // global address of chunk q (valid while q < fullChunks)
+    u32 sdst = (q & (RING / 4 - 1)) * (THREADS * 16);  // its ring slot (byte offset from ringLo)
     auto top_up = [&]() {
         u32 const kk = word_index();
-        if (4 * q <= kk + 14) {
-            if (q < fullChunks) stage_async(q); else stage_sync(q);
-            q++;
+        u32 v = 4 * q - kk;
+        if (v <= 14) {
+            if (q < fullChunks) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" :: "r"(ringLo + sdst), "l"(gsrc) : "memory");
+            else stage_sync(q);
+            q++; gsrc -= 16; sdst = (sdst + THREADS * 16) & (RING * THREADS * 4 - 1); v += 4;
         }
-        if (q >= fullChunks) asm volatile("cp.async.wait_group 0;" ::: "memory");   // tail of the stream: chunks come through registers, nothing may stay pending
-        else asm volatile("cp.async.wait_group 2;" ::: "memory");
+        if (__builtin_expect(v < 13, 0)) {            // emergency: the consumer outruns one chunk per call
+            while (4 * q - kk <= 14) { stage_sync(q); q++; gsrc -= 16; sdst = (sdst + THREADS * 16) & (RING * THREADS * 4 - 1); }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if (q >= fullChunks) asm volatile("cp.async.wait_group 0;" ::: "memory");   // tail of the stream: chunks come through registers
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
     };
     // One symbol, branch-free: E = nbBits | symbol << 8, window advanced.  Integer work is split between the ALU pipe
     // (and / setp / funnel shifts) and the FMA pipe (mad.hi / mad.lo do the two shifts-and-adds that form the addresses):
@@ -345,7 +354,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
             u32 o[4], e0, e1;
             #pragma unroll
             for (int h = 0; h < 4; h++) {
-                if ((h & 1) == 0) top_up();              // every 8 symbols
+                if (h == 0) top_up();                    // every 16 symbols
                 u32 t;
                 HUFD_LOOKUP(e0); HUFD_LOOKUP(e1); r += e0 + e1; HUFD_REFILL();
                 t = __byte_perm(e0, e1, 0x0051);                        // {sym0, sym1, x, x}
