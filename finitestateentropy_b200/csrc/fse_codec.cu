@@ -16,6 +16,7 @@
 // Tables live in shared memory (CTable 10 KB, DTable 16 KB at tableLog 12); that footprint bounds
 // the number of resident blocks per SM and with it the throughput -- far below the HBM roofline,
 // as SURVEY.md section 7.3 anticipates.
+#include <cstdlib>
 #include "common.cuh"
 #include "fse_dev.cuh"
 #include "bitsrc_dev.cuh"
@@ -442,6 +443,267 @@ fse_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
 }
 
 // =================================================================================================
+// decode, batch kernel.  A tANS decode is one serial chain per block (state -> cell -> bits -> state) that the
+// format does not let us split, and its table is what limits how many chains an SM keeps resident.  So: a CTA
+// owns DK blocks, its four warps parse the headers and build the tables (bytes: 12-bit next-state base + 4-bit
+// nbBits in a u16 cell plus a separate symbol byte -- 12 KB instead of 16 KB per block), then warp 0 runs ONE LANE
+// PER BLOCK.  A lane reads its stream straight from global memory through a 96-bit register window (aligned
+// 32-bit words, next word prefetched) with a bit cursor, so a symbol costs two table loads and ~8 ALU ops.
+// The reference's reader is byte-granular (BIT_reloadDStream); its bookkeeping only matters near the two ends
+// of the stream, so the lane runs check-free chunks whose length is bounded so that every reload the reference
+// would do in between returns "unfinished" (ptr stays >= start + 8) and the output bound holds, then hands the
+// last few bytes to the exact byte-granular model (bitsrc_dev.cuh) which also produces the verdicts.
+// =================================================================================================
+constexpr int DTHREADS = 128;
+template <bool WIDE> struct DecCta {
+    static constexpr unsigned DK = WIDE ? 3 : 8;                    // blocks per CTA; two CTAs per SM
+    static constexpr unsigned MSV = DecCfg<WIDE>::MSV, CELLS = DecCfg<WIDE>::CELLS;
+    static constexpr unsigned TAB_BYTES = WIDE ? CELLS * 4 : CELLS * 3;
+    static constexpr unsigned WB = WIDE ? 7 : 6;                    // most stream bytes one 4-symbol iteration can retire ((7 + 4 * tableLog) >> 3)
+    struct alignas(16) Scratch { short norm[MSV + 1]; u16 cum[MSV + 3]; u16 nextOf[MSV + 1]; };
+    struct alignas(16) Smem {
+        u8 tab[DK][TAB_BYTES];
+        Scratch scratch[DTHREADS / 32];
+        u32 go[DK], tl[DK], fast[DK], hdr[DK];
+    };
+};
+__device__ __forceinline__ u32 lds_u16(u32 addr) { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ u32 lds_u8(u32 addr)  { u32 v; asm volatile("ld.shared.u8 %0, [%1];"  : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ u32 lds_u32(u32 addr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+// Table of one block, one warp.  bytes: tab = u16 cell[size] (nextState base | nbBits << 12) then u8 symbol[size];
+// U16: u32 cell[size] (base | nbBits << 16 | symbol << 20).  Same construction as warp_build_dtable.
+template <bool WIDE>
+__device__ inline u64 warp_build_dtable_split(typename DecCta<WIDE>::Scratch& w, u8* tab, unsigned msv, unsigned tl, unsigned& fastOut)
+{
+    unsigned const lane = lane_id();
+    u32 const size = 1u << tl;
+    if (msv > DecCfg<WIDE>::MSV) return err(E_MSV_TOO_LARGE);
+    if (tl > DecCfg<WIDE>::TL) return err(E_TLOG_TOO_LARGE);
+    unsigned fast = 1;
+    if (lane == 0) {
+        u32 acc = 0;
+        for (u32 s = 0; s <= msv; s++) {
+            w.cum[s] = (u16)acc;
+            int const n = w.norm[s];
+            if (n == -1) w.nextOf[s] = 1;
+            else { if (n >= (int)(1u << (tl - 1))) fast = 0; w.nextOf[s] = (u16)n; if (n > 0) acc += (u32)n; }
+        }
+        w.cum[msv + 1] = (u16)acc;
+    }
+    fastOut = __shfl_sync(FULL, fast, 0);
+    __syncwarp();
+    u16* const t16 = reinterpret_cast<u16*>(tab);
+    u8*  const s8  = tab + 2 * DecCfg<false>::CELLS;
+    u32* const c32 = reinterpret_cast<u32*>(tab);
+    bool const closed = warp_spread(w.norm, w.cum, msv, tl, [&](u32 cell, u32 sym) { if (WIDE) c32[cell] = sym; else s8[cell] = (u8)sym; });
+    __syncwarp();
+    if (!closed) return err(E_GENERIC);
+    for (u32 u0 = 0; u0 < size; u0 += 32) {                       // the k-th cell (ascending) of symbol s gets x = norm[s] + k  (fse_decompress.c:117-124)
+        u32 const u = u0 + lane;
+        u32 const sym = WIDE ? c32[u] : (u32)s8[u];
+        u32 const peers = __match_any_sync(FULL, sym);
+        u32 const x = w.nextOf[sym] + __popc(peers & ((1u << lane) - 1));
+        __syncwarp();
+        if ((peers >> lane) == 1u) w.nextOf[sym] = (u16)(w.nextOf[sym] + __popc(peers));
+        u32 const nb = tl - hibit(x);
+        u32 const ns = ((x << nb) - size) & 0xFFFF;
+        if (WIDE) c32[u] = ns | (nb << 16) | (sym << 20); else t16[u] = (u16)(ns | (nb << 12));
+        __syncwarp();
+    }
+    return 0;
+}
+
+// exact-model steps on the split table (tail of a stream)
+template <bool WIDE>
+__device__ __forceinline__ u32 tab_step(u32& state, BitSrc& b, u32 tabAddr, bool fast)
+{
+    if (WIDE) {
+        u32 const cell = lds_u32(tabAddr + 4 * state);
+        state = (cell & 0xFFFF) + (u32)bs_read(b, (cell >> 16) & 0xF);
+        return cell >> 20;
+    }
+    u32 const cell = lds_u16(tabAddr + 2 * state);
+    u32 const sym = lds_u8(tabAddr + 2 * DecCfg<false>::CELLS + state);
+    u32 const nb = cell >> 12;
+    state = (cell & 0xFFF) + (u32)(fast ? bs_read_fast(b, nb) : bs_read(b, nb));
+    return sym;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(DTHREADS, 2)
+fse_decode_cta_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf, const u64* __restrict__ csizes,
+                      u64* __restrict__ results, const u8* __restrict__ orig)
+{
+    typedef DecCta<WIDE> C;
+    constexpr unsigned DK = C::DK;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename C::Smem& sm = *reinterpret_cast<typename C::Smem*>(smem_raw);
+    unsigned const lane = lane_id(), warp = threadIdx.x >> 5;
+    u32 const b0 = blockIdx.x * DK;
+    u32 const nHere = g.nBlocks - b0 < DK ? g.nBlocks - b0 : DK;
+
+    // ---- phase 1: stored-block conventions, header, table: one warp per block ----
+    if (threadIdx.x < DK) sm.go[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 blk = warp; blk < nHere; blk += DTHREADS / 32) {
+        u32 const b = b0 + blk;
+        u32 const n = block_len(g, b);
+        u64 const cs = csizes[b];
+        u8* const out = dst + (u64)b * g.blockSize;
+        const u8* const c = cbuf + (u64)b * g.slot;
+        if (is_err(cs)) { if (lane == 0) results[b] = cs; continue; }
+        if (cs == 0 || (cs == 1 && !WIDE)) {                        // the harness' conventions for stored blocks (bench.c:393-402)
+            if (orig) {
+                const u8* const o = orig + (u64)b * g.blockSize;
+                if (cs == 0) for (u32 i = lane; i < n; i += 32) out[i] = o[i];
+                else { u8 const v = o[0]; for (u32 i = lane; i < n; i += 32) out[i] = v; }
+            }
+            if (lane == 0) results[b] = orig ? n : 0;
+            continue;
+        }
+        typename C::Scratch& w = sm.scratch[warp];
+        u64 h = 0; unsigned tl = 0, msv = C::MSV;
+        if (lane == 0) {
+            if (WIDE && cs < 2) h = err(E_SRC_WRONG);                                   // fseU16.c:317
+            else h = d_read_ncount(w.norm, &msv, &tl, c, cs);
+            if (!WIDE && !is_err(h) && tl > FSE_MAX_TLOG) h = err(E_TLOG_TOO_LARGE);    // fse_decompress.c:266
+        }
+        h = __shfl_sync(FULL, h, 0); tl = __shfl_sync(FULL, tl, 0); msv = __shfl_sync(FULL, msv, 0);
+        if (is_err(h)) { if (lane == 0) results[b] = h; continue; }
+        __syncwarp();
+        unsigned fast = 0;
+        u64 const e = warp_build_dtable_split<WIDE>(w, sm.tab[blk], msv, tl, fast);
+        if (is_err(e)) { if (lane == 0) results[b] = e; continue; }
+        if (lane == 0) { sm.go[blk] = 1; sm.tl[blk] = tl; sm.fast[blk] = fast; sm.hdr[blk] = (u32)h; }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp != 0) return;
+
+    // ---- phase 2: one lane per block ----
+    bool const mine = lane < DK && sm.go[lane < DK ? lane : 0];
+    u32 const blk = mine ? lane : 0;
+    u32 const b = b0 + blk;
+    u32 const tl = sm.tl[blk];
+    bool const fastMode = sm.fast[blk] != 0;
+    u32 const tabAddr = (u32)__cvta_generic_to_shared(sm.tab[blk]);
+    u32 const symAddr = tabAddr + 2 * DecCfg<false>::CELLS;
+    u32 const nBytes = mine ? block_len(g, b) : 0;
+    long long const omax = WIDE ? nBytes / 2 : nBytes;              // symbols
+    u8* const out = dst + (u64)b * g.blockSize;
+    const u8* const cs0 = cbuf + (u64)b * g.slot;
+    u64 const lowest = reinterpret_cast<u64>(cs0) & ~15ull;          // nothing below the block's own slot is ever read
+    BitSrc bs; bs.s = cs0; bs.len = 0; bs.at = 0; bs.w = 0; bs.used = 0;
+    u32 s1 = 0, s2 = 0;
+    long long op = 0;
+    u64 ret = 0;
+    int mode = mine ? 0 : 2;                                        // 0 = chunked fast region, 1 = exact tail, 2 = finished
+    bool openErr = false;
+    if (mine) {
+        u64 const cs = csizes[b]; u32 const h = sm.hdr[blk];
+        u64 const e = bs_open(bs, cs0 + h, cs - h);
+        if (!WIDE) {
+            if (is_err(e)) { ret = e; mode = 2; }
+            else { s1 = (u32)bs_read(bs, tl); bs_refill(bs); s2 = (u32)bs_read(bs, tl); bs_refill(bs); }
+        } else {
+            if (cs - h < 1) { ret = err(E_CORRUPT); mode = 2; }      // the reference dereferences a NULL stream here (documented deviation)
+            else { openErr = is_err(e); s1 = (u32)bs_read(bs, tl); bs_refill(bs); }    // fseU16.c:286 ignores the verdict
+        }
+    }
+    bool const al4 = ((reinterpret_cast<u64>(out) & 3) == 0);
+    (void)openErr;
+
+    // physical window: w0 (highest) : w1 : w2, cursor k bits into w0:w1, q = prefetched word below w2, p = address below q
+    u32 w0 = 0, w1 = 0, w2 = 0, q = 0, k = 0; u64 p = 0;
+    bool windowed = false;
+    auto ldw = [&](u64 a) -> u32 { return a >= lowest ? __ldg(reinterpret_cast<const u32*>(a)) : 0u; };
+    for (;;) {
+        // chunk length: every reload in between must see ptr >= start + 8, every iteration needs 4 output slots
+        u32 m = 0;
+        if (mode == 0) {
+            if (bs.len >= 8 && bs.at >= 8 && bs.used <= 7) {
+                u64 const ms = (bs.at - 8) / C::WB, mo = (u64)((omax - op) / 4);
+                m = (u32)(ms < mo ? ms : mo);
+            }
+            if (m == 0) mode = 1;
+        }
+        u32 mm = mode == 0 ? m : 0xFFFFFFFFu;
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) mm = min(mm, __shfl_xor_sync(FULL, mm, d));
+        if (mm == 0xFFFFFFFFu) break;
+        if (mode == 0) {
+            if (!windowed) {                                        // stand the window on (at, used)
+                u64 const A = reinterpret_cast<u64>(bs.s) + bs.at + 8;
+                u64 const top4 = (A + 3) & ~3ull;
+                k = (u32)(8 * (top4 - A)) + bs.used;               // <= 31
+                w0 = ldw(top4 - 4); w1 = ldw(top4 - 8); w2 = ldw(top4 - 12); q = ldw(top4 - 16); p = top4 - 20;
+                windowed = true;
+            }
+            u64 const p0 = p; u32 const k0 = k;
+#define FSEB_NORM() do { bool const adv_ = k >= 32; if (adv_) { w0 = w1; w1 = w2; w2 = q; q = ldw(p); p -= 4; k -= 32; } } while (0)
+#define FSEB_PSTEP(ST, SYM, FIRST) do { \
+                u32 cell_, nb_, base_; \
+                if (WIDE) { cell_ = lds_u32(tabAddr + 4 * ST); SYM = cell_ >> 20; nb_ = (cell_ >> 16) & 0xF; base_ = cell_ & 0xFFFF; } \
+                else { cell_ = lds_u16(tabAddr + 2 * ST); SYM = lds_u8(symAddr + ST); nb_ = cell_ >> 12; base_ = cell_ & 0xFFF; } \
+                u32 const va_ = __funnelshift_l(w1, w0, k); \
+                u32 const v_ = FIRST ? va_ : (k < 32 ? va_ : __funnelshift_l(w2, w1, k)); \
+                ST = base_ + __funnelshift_l(v_, 0, nb_); k += nb_; } while (0)
+            #pragma unroll 1
+            for (u32 it = 0; it < mm; it++) {
+                u32 a0, a1, a2, a3;
+                if (!WIDE) {
+                    FSEB_PSTEP(s1, a0, true); FSEB_PSTEP(s2, a1, false); FSEB_NORM();
+                    FSEB_PSTEP(s1, a2, true); FSEB_PSTEP(s2, a3, false); FSEB_NORM();
+                    if (al4) *reinterpret_cast<u32*>(out + op) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+                    else { out[op] = (u8)a0; out[op + 1] = (u8)a1; out[op + 2] = (u8)a2; out[op + 3] = (u8)a3; }
+                } else {
+                    FSEB_PSTEP(s1, a0, true); FSEB_PSTEP(s1, a1, false); FSEB_NORM();
+                    FSEB_PSTEP(s1, a2, true); FSEB_PSTEP(s1, a3, false); FSEB_NORM();
+                    u16* const o16 = reinterpret_cast<u16*>(out) + op;
+                    if (al4) { reinterpret_cast<u32*>(o16)[0] = a0 | (a1 << 16); reinterpret_cast<u32*>(o16)[1] = a2 | (a3 << 16); }
+                    else { o16[0] = (u16)a0; o16[1] = (u16)a1; o16[2] = (u16)a2; o16[3] = (u16)a3; }
+                }
+                op += 4;
+            }
+#undef FSEB_PSTEP
+#undef FSEB_NORM
+            u64 const tot = bs.used + 8 * (p0 - p) + k - k0;       // bits retired in this chunk, carried into the byte-granular counters
+            bs.at -= tot >> 3; bs.used = (unsigned)(tot & 7);
+        }
+    }
+    // ---- exact tail on the byte-granular model ----
+    if (mode == 1) {
+        if (windowed) bs.w = ld64u(bs.s + bs.at);
+        if (!WIDE) {
+            for (; (bs_refill(bs) == SRC_MORE) & (op < omax - 3); op += 4) {          // fse_decompress.c:206-220
+                out[op]     = (u8)tab_step<WIDE>(s1, bs, tabAddr, fastMode);
+                out[op + 1] = (u8)tab_step<WIDE>(s2, bs, tabAddr, fastMode);
+                out[op + 2] = (u8)tab_step<WIDE>(s1, bs, tabAddr, fastMode);
+                out[op + 3] = (u8)tab_step<WIDE>(s2, bs, tabAddr, fastMode);
+            }
+            for (;;) {                                                                 // :222-235
+                if (op > omax - 2) { ret = err(E_DST_TOO_SMALL); break; }
+                out[op++] = (u8)tab_step<WIDE>(s1, bs, tabAddr, fastMode);
+                if (bs_refill(bs) == SRC_OVER) { out[op++] = (u8)tab_step<WIDE>(s2, bs, tabAddr, fastMode); ret = (u64)op; break; }
+                if (op > omax - 2) { ret = err(E_DST_TOO_SMALL); break; }
+                out[op++] = (u8)tab_step<WIDE>(s2, bs, tabAddr, fastMode);
+                if (bs_refill(bs) == SRC_OVER) { out[op++] = (u8)tab_step<WIDE>(s1, bs, tabAddr, fastMode); ret = (u64)op; break; }
+            }
+        } else {
+            u16* const o16 = reinterpret_cast<u16*>(out);
+            while (bs_refill(bs) < SRC_DONE && op < omax) o16[op++] = (u16)tab_step<WIDE>(s1, bs, tabAddr, false);    // fseU16.c:289-293
+            if (!bs_exhausted(bs)) ret = err(E_CORRUPT);                                                            // :295
+            else {
+                while (s1 && op < omax) o16[op++] = (u16)tab_step<WIDE>(s1, bs, tabAddr, false);                     // :297-298
+                ret = s1 ? err(E_CORRUPT) : (u64)op * 2;
+            }
+        }
+    }
+    if (mine) results[b] = ret;
+}
+
+// =================================================================================================
 // encode
 // =================================================================================================
 template <bool WIDE> struct EncCfg;
@@ -499,67 +761,95 @@ __device__ __forceinline__ void warp_emit(EncWarp<WIDE>& w, u32 cnt, u32& carry,
     }
 }
 
+// Scratch of the front half of one block's compression.  `count` and `start` may alias the symbol-transform area
+// of `ct` (they are dead before it is written); everything is shared memory.
 template <bool WIDE>
-__global__ void __launch_bounds__(THREADS)
-fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
-                  unsigned msvReq, unsigned tlogReq)
+struct EncFront {
+    u32* ct; u32* count; u32* start; short* norm; u16* cum; typename EncCfg<WIDE>::sym_t* cellSym;
+};
+
+// Everything FSE_compress_wksp / FSE_compressU16 do before the first FSE_encodeSymbol: argument checks, histogram,
+// rle / not-compressible verdicts, normalisation, the NCount header (written to d) and the CTable.  One warp.
+// Returns true when the payload must be coded (hSize, tl set); false when `verdict` is already the block's result.
+template <bool WIDE>
+__device__ inline bool warp_encode_front(const EncFront<WIDE>& w, const typename EncCfg<WIDE>::sym_t* s, u32 n, u8* d, u64 cap,
+                                         unsigned msvReq, unsigned tlogReq, u64& verdict, u32& hSizeOut, u32& tlOut, u32 chainBase = 0)
 {
     typedef typename EncCfg<WIDE>::sym_t sym_t;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    EncWarp<WIDE>& w = reinterpret_cast<EncWarp<WIDE>*>(smem_raw)[threadIdx.x >> 5];
     unsigned const lane = lane_id();
-    u32 const b = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (b >= g.nBlocks) return;
-    u32 const nBytes = block_len(g, b);
-    u32 const n = WIDE ? nBytes / 2 : nBytes;                        // symbols
-    const sym_t* const s = reinterpret_cast<const sym_t*>(src + (u64)b * g.blockSize);
-    u8* const d = cbuf + (u64)b * g.slot;
-    u64 const cap = g.slot;
     unsigned const MSVMAX = EncCfg<WIDE>::MSV;
-#define FSEB_DONE(v) do { if (lane == 0) csizes[b] = (v); return; } while (0)
-
+#define FRONT_DONE(v) do { verdict = (v); return false; } while (0)
     // ---- argument checks (fse_compress.c:645-649,691 ; fseU16.c:216-220) ----
     unsigned msv = msvReq, tl = tlogReq;
     if (!WIDE) {
-        if (tl > FSE_MAX_TLOG) FSEB_DONE(err(E_TLOG_TOO_LARGE));
-        if (tl == 0) FSEB_DONE(err(E_TLOG_TOO_LARGE));               // FSE_WKSP_SIZE_U32(0,..) shifts by -1: the reference (gcc/x86-64) reports tableLog_tooLarge
-        if ((u64)14340 < (u64)1 + (1ull << (tl - 1)) + ((u64)msv + 1) * 2 + 1024) FSEB_DONE(err(E_TLOG_TOO_LARGE));   // :645 vs the stack workspace of :679-685
-        if (n <= 1) FSEB_DONE(0);
+        if (tl > FSE_MAX_TLOG) FRONT_DONE(err(E_TLOG_TOO_LARGE));
+        if (tl == 0) FRONT_DONE(err(E_TLOG_TOO_LARGE));               // FSE_WKSP_SIZE_U32(0,..) shifts by -1: the reference (gcc/x86-64) reports tableLog_tooLarge
+        if ((u64)14340 < (u64)1 + (1ull << (tl - 1)) + ((u64)msv + 1) * 2 + 1024) FRONT_DONE(err(E_TLOG_TOO_LARGE));   // :645 vs the stack workspace of :679-685
+        if (n <= 1) FRONT_DONE(0);
         if (!msv) msv = FSE_MAX_SV;
         if (msv > FSE_MAX_SV) msv = FSE_MAX_SV;                      // HIST_count_wksp clamps (hist.c:171)
     } else {
-        if (n <= 1) FSEB_DONE(n);
+        if (n <= 1) FRONT_DONE(n);
         if (!msv) msv = U16_MAX_SV;
         if (!tl) tl = U16_DEF_TLOG;
-        if (msv > U16_MAX_SV) FSEB_DONE(err(E_MSV_TOO_LARGE));
-        if (tl > U16_MAX_TLOG) FSEB_DONE(err(E_TLOG_TOO_LARGE));
+        if (msv > U16_MAX_SV) FRONT_DONE(err(E_MSV_TOO_LARGE));
+        if (tl > U16_MAX_TLOG) FRONT_DONE(err(E_TLOG_TOO_LARGE));
     }
-    // ---- histogram ----
-    for (u32 i = lane; i <= MSVMAX; i += 32) w.count[i] = 0;
-    __syncwarp();
+    // ---- histogram: four interleaved copies (lane & 3) in the not-yet-built table area, 16-byte loads, 4 in flight ----
     u32 over = 0;
-    for (u32 i0 = 0; i0 < n; i0 += 32) {
-        u32 const i = i0 + lane;
-        u32 const v = (i < n) ? (u32)s[i] : 0xFFFFFFFFu;
-        u32 const peers = __match_any_sync(FULL, v);
-        if (i < n) {
-            if (v > (WIDE ? msv : 255u)) over = 1;
-            else if ((peers >> lane) == 1u) atomicAdd(&w.count[v], (u32)__popc(peers));
+    {
+        u32* const sub = w.ct;
+        for (u32 i = lane; i < 4 * (MSVMAX + 1); i += 32) sub[i] = 0;
+        __syncwarp();
+        u32* const mine = sub + (lane & 3) * (MSVMAX + 1);
+        u32 const lim = WIDE ? msv : 255u;
+        auto add1 = [&](u32 v, u32 k) { if (WIDE && v > lim) over = 1; else atomicAdd(&mine[v], k); };
+        const u8* const sb = reinterpret_cast<const u8*>(s);
+        u32 const nB = WIDE ? 2 * n : n;
+        u32 const head = min(nB, (u32)((16 - (reinterpret_cast<u64>(sb) & 15)) & 15));
+        for (u32 k = lane; k < head / sizeof(sym_t); k += 32) add1(s[k], 1);
+        u32 const nvec = (nB - head) / 16;
+        const uint4* const gv = reinterpret_cast<const uint4*>(sb + head);
+        for (u32 v0 = 0; v0 < nvec; v0 += 128) {
+            uint4 x[4];
+            #pragma unroll
+            for (int h = 0; h < 4; h++) { u32 const vi = v0 + 32 * h + lane; x[h] = (vi < nvec) ? __ldg(gv + vi) : make_uint4(0, 0, 0, 0); }
+            #pragma unroll
+            for (int h = 0; h < 4; h++) {
+                if (v0 + 32 * h + lane >= nvec) continue;
+                u32 const wd[4] = { x[h].x, x[h].y, x[h].z, x[h].w };
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 const y = wd[k];
+                    if (WIDE) {
+                        u32 const a0 = y & 0xFFFFu, a1 = y >> 16;
+                        if (a0 == a1) add1(a0, 2); else { add1(a0, 1); add1(a1, 1); }
+                    } else {
+                        u32 const b0 = y & 0xFF, b1 = (y >> 8) & 0xFF, b2 = (y >> 16) & 0xFF, b3 = y >> 24;
+                        if ((b0 == b1) & (b1 == b2) & (b2 == b3)) add1(b0, 4);
+                        else { add1(b0, 1); add1(b1, 1); add1(b2, 1); add1(b3, 1); }
+                    }
+                }
+            }
         }
+        for (u32 k = (head + nvec * 16) / sizeof(sym_t) + lane; k < n; k += 32) add1(s[k], 1);
+        __syncwarp();
+        for (u32 i = lane; i <= MSVMAX; i += 32)
+            w.count[i] = sub[i] + sub[(MSVMAX + 1) + i] + sub[2 * (MSVMAX + 1) + i] + sub[3 * (MSVMAX + 1) + i];
     }
     __syncwarp();
     over = __any_sync(FULL, over);
-    if (WIDE && over) FSEB_DONE(err(E_MSV_TOO_SMALL));               // fseU16.c:131
+    if (WIDE && over) FRONT_DONE(err(E_MSV_TOO_SMALL));               // fseU16.c:131
     u32 top = 0, best = 0;
     for (u32 i = lane; i <= (WIDE ? msv : 255u); i += 32) { u32 const c = w.count[i]; if (c) top = i; best = c > best ? c : best; }
     #pragma unroll
     for (int dlt = 16; dlt; dlt >>= 1) { top = max(top, __shfl_xor_sync(FULL, top, dlt)); best = max(best, __shfl_xor_sync(FULL, best, dlt)); }
-    if (!WIDE && msv < 255 && top > msv) FSEB_DONE(err(E_MSV_TOO_SMALL));            // hist.c:128
+    if (!WIDE && msv < 255 && top > msv) FRONT_DONE(err(E_MSV_TOO_SMALL));            // hist.c:128
     msv = top;
-    if (best == n) FSEB_DONE(1);                                      // rle
+    if (best == n) FRONT_DONE(1);                                      // rle
     if (!WIDE) {
-        if (best == 1) FSEB_DONE(0);
-        if (best < (n >> 7)) FSEB_DONE(0);
+        if (best == 1) FRONT_DONE(0);
+        if (best < (n >> 7)) FRONT_DONE(0);
     }
     // ---- normalise + header (one lane) ----
     tl = d_optimal_tablelog(tl, n, msv, 2);
@@ -569,7 +859,7 @@ fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, 
         if (!is_err(hdr)) hdr = d_write_ncount(d, cap, w.norm, msv, tl);
     }
     hdr = __shfl_sync(FULL, hdr, 0);
-    if (is_err(hdr)) FSEB_DONE(hdr);
+    if (is_err(hdr)) FRONT_DONE(hdr);
     u32 const hSize = (u32)hdr;
     // ---- CTable (fse_compress.c:66-169) ----
     u32 const size = 1u << tl;
@@ -603,6 +893,16 @@ fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, 
             u32 total = 0;
             for (u32 q = 0; q <= msv; q++) {
                 int const nn = w.norm[q];
+                if (chainBase) {                                    // chain form: { byte address of next[deltaFindState], maxBitsOut << 16 | minStatePlus }
+                    if (nn == 0) { tt[2 * q] = chainBase; tt[2 * q + 1] = (tl << 16) | size; continue; }
+                    if (nn == -1 || nn == 1) { tt[2 * q] = chainBase + 2 * (total - 1); tt[2 * q + 1] = (tl << 16) | size; total++; }
+                    else {
+                        u32 const maxOut = tl - hibit((u32)nn - 1);
+                        tt[2 * q] = chainBase + 2 * (total - (u32)nn); tt[2 * q + 1] = (maxOut << 16) | ((u32)nn << maxOut);
+                        total += (u32)nn;
+                    }
+                    continue;
+                }
                 if (nn == 0) { tt[2 * q + 1] = ((tl + 1) << 16) - size; tt[2 * q] = 0; continue; }
                 if (nn == -1 || nn == 1) { tt[2 * q + 1] = (tl << 16) - size; tt[2 * q] = total - 1; total++; }
                 else {
@@ -614,6 +914,33 @@ fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, 
         }
     }
     __syncwarp();
+    hSizeOut = hSize; tlOut = tl;
+    return true;
+#undef FRONT_DONE
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(THREADS)
+fse_encode_kernel(BatchGeom g, u32 firstBlock, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
+                  unsigned msvReq, unsigned tlogReq)
+{
+    typedef typename EncCfg<WIDE>::sym_t sym_t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncWarp<WIDE>& w = reinterpret_cast<EncWarp<WIDE>*>(smem_raw)[threadIdx.x >> 5];
+    unsigned const lane = lane_id();
+    u32 const b = firstBlock + blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (b >= g.nBlocks) return;
+    u32 const nBytes = block_len(g, b);
+    u32 const n = WIDE ? nBytes / 2 : nBytes;                        // symbols
+    const sym_t* const s = reinterpret_cast<const sym_t*>(src + (u64)b * g.blockSize);
+    u8* const d = cbuf + (u64)b * g.slot;
+    u64 const cap = g.slot;
+#define FSEB_DONE(v) do { if (lane == 0) csizes[b] = (v); return; } while (0)
+
+    EncFront<WIDE> f; f.ct = w.ct; f.count = w.count; f.start = w.start; f.norm = w.norm; f.cum = w.cum; f.cellSym = w.cellSym;
+    u64 verdict = 0; u32 hSize = 0, tl = 0;
+    if (!warp_encode_front<WIDE>(f, s, n, d, cap, msvReq, tlogReq, verdict, hSize, tl)) FSEB_DONE(verdict);
+    u32 const size = 1u << tl;
     // ---- encode (fse_compress.c:554-611 ; U16: fseU16.c:150-200) ----
     u64 const scap = cap - hSize;                                    // capacity seen by the stream writer
     bool const usable = scap > 8;
@@ -699,6 +1026,279 @@ fse_encode_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, 
 #undef FSEB_DONE
 }
 
+
+// =================================================================================================
+// encode, batch kernel.  The tANS chain is a serial dependency (state -> table -> state, ~50 cycles per symbol) and its
+// tables (10 KB per block) are what limits how many chains an SM can keep resident, so the work is arranged
+// around the chains: one CTA owns EK blocks; all warps run the front half (histogram .. CTable) of the blocks,
+// then warp 0 becomes the CHAIN warp -- lane pair (2k, 2k+1) carries the two interleaved states of block k
+// (U16: lane k carries the single state) and does nothing but table walks, dropping one (state, nbBits) record per
+// symbol into a shared-memory ring -- while warps 1..7 are EMITTERS that turn ring groups into stream words
+// (prefix scan of bit counts, OR into a staging word array, coalesced word stores).  Ring groups are handed
+// over with named barriers (two buffers).  Only full blocks whose size is a multiple of 64 bytes and that
+// start 16-byte aligned come here; everything else takes the warp-per-block kernel above.
+// =================================================================================================
+constexpr int ETHREADS = 256;
+constexpr int GSTEPS = 32;             // chain steps per ring group
+template <bool WIDE, int EK> struct EncCta {         // EK = blocks per CTA (16: one CTA per SM; 8: two)
+    typedef typename EncCfg<WIDE>::sym_t sym_t;
+    static constexpr unsigned CH = WIDE ? 1 : 2;
+    static constexpr unsigned MSV = EncCfg<WIDE>::MSV, CELLS = EncCfg<WIDE>::CELLS;
+    static constexpr unsigned CT_WORDS = ((2 + CELLS / 2 + 2 * (MSV + 1) + 8) + 3) & ~3u;    // u32 per block, 16-byte multiple
+    static constexpr unsigned BUILDERS = WIDE ? EK / 4 : EK / 2;
+    static constexpr unsigned RING_STRIDE = GSTEPS * CH + 2;                                 // u32 per block per buffer (+2 skews the banks)
+    struct alignas(16) Scratch { short norm[MSV + 1]; u16 cum[MSV + 3]; sym_t cellSym[CELLS]; };
+    struct alignas(16) Smem {
+        u32 ct[EK * CT_WORDS];
+        u32 ring[2 * EK * RING_STRIDE];
+        u32 words[8 * 32];
+        u32 active[EK], hSize[EK], tl[EK];
+        Scratch scratch[BUILDERS];
+    };
+};
+// named barriers 1,2 = ring buffer 0,1 full ; 3,4 = ring buffer 0,1 drained (immediate ids: the CTA then owns 5 barriers, not 16)
+__device__ __forceinline__ void bar_sync(int id)
+{
+    switch (id) {
+    case 1: asm volatile("bar.sync 1, 256;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 2, 256;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 3, 256;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 256;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void bar_arrive(int id)
+{
+    switch (id) {
+    case 1: asm volatile("bar.arrive 1, 256;" ::: "memory"); break;
+    case 2: asm volatile("bar.arrive 2, 256;" ::: "memory"); break;
+    case 3: asm volatile("bar.arrive 3, 256;" ::: "memory"); break;
+    default: asm volatile("bar.arrive 4, 256;" ::: "memory"); break;
+    }
+}
+static_assert(ETHREADS == 256, "barrier counts are spelled out");
+__device__ __forceinline__ uint2 lds_v2(u32 addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+
+// appends CH records per lane (lane order, r0 before r1) to one block's stream; same stream state as warp_emit
+template <bool WIDE>
+__device__ __forceinline__ void emit_group(u32 r0, u32 r1, u32* words, u32& carry, u32& carryBits, u32& wpos,
+                                           u32* base32, u32 capWords, u32 mis, u32& totalBits)
+{
+    unsigned const lane = lane_id();
+    u32 const nb0 = r0 >> 16, v0 = r0 & ((1u << nb0) - 1);
+    u32 nb = nb0, val = v0;
+    if (!WIDE) { u32 const nb1 = r1 >> 16; val |= (r1 & ((1u << nb1) - 1)) << nb0; nb += nb1; }
+    u32 incl = nb;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 const t = __shfl_up_sync(FULL, incl, d); if (lane >= (unsigned)d) incl += t; }
+    u32 const sum = __shfl_sync(FULL, incl, 31);
+    u32 const off = carryBits + incl - nb;
+    if (lane < 28) words[lane] = (lane == 0) ? carry : 0u;
+    __syncwarp();
+    if (nb) {
+        u64 const v = (u64)val << (off & 31);
+        atomicOr(&words[off >> 5], (u32)v);
+        if ((u32)(v >> 32)) atomicOr(&words[(off >> 5) + 1], (u32)(v >> 32));
+    }
+    __syncwarp();
+    u32 const tot = carryBits + sum;
+    u32 const full = tot >> 5;
+    if (lane < full && wpos + lane < capWords) {
+        if (wpos + lane == 0 && mis) {                              // word 0 also covers `mis` header bytes: leave them alone
+            u8* const p8 = reinterpret_cast<u8*>(base32);
+            for (u32 i = mis; i < 4; i++) p8[i] = (u8)(words[0] >> (8 * i));
+        } else base32[wpos + lane] = words[lane];
+    }
+    carry = words[full]; carryBits = tot & 31; wpos += full; totalBits += sum;
+    __syncwarp();
+}
+
+template <bool WIDE, int EK>
+__global__ void __launch_bounds__(ETHREADS, 16 / EK)
+fse_encode_cta_kernel(BatchGeom g, u32 nFast, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
+                      unsigned msvReq, unsigned tlogReq)
+{
+    typedef EncCta<WIDE, EK> C;
+    typedef typename C::sym_t sym_t;
+    constexpr unsigned CH = C::CH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename C::Smem& sm = *reinterpret_cast<typename C::Smem*>(smem_raw);
+    unsigned const lane = lane_id(), warp = threadIdx.x >> 5;
+    u32 const b0 = blockIdx.x * EK;
+    u32 const nHere = nFast - b0 < (u32)EK ? nFast - b0 : (u32)EK;
+    u32 const nBytes = (u32)g.blockSize;
+    u32 const n = WIDE ? nBytes / 2 : nBytes;
+    u64 const cap = g.slot;
+
+    // ---- phase 1: front half of every block, one warp per block ----
+    if (threadIdx.x < EK) sm.active[threadIdx.x] = 0;
+    __syncthreads();
+    if (warp < C::BUILDERS) {
+        for (u32 blk = warp; blk < nHere; blk += C::BUILDERS) {
+            u32 const b = b0 + blk;
+            EncFront<WIDE> f;
+            f.ct = sm.ct + blk * C::CT_WORDS + 1;                  // +1: the symbol transforms (8-byte pairs) land 8-byte aligned
+            f.count = f.ct + 1 + C::CELLS / 2; f.start = f.count + C::MSV + 1;      // dead before the transforms are written
+            f.norm = sm.scratch[warp].norm; f.cum = sm.scratch[warp].cum; f.cellSym = sm.scratch[warp].cellSym;
+            u8* const d = cbuf + (u64)b * g.slot;
+            u64 verdict = 0; u32 hSize = 0, tl = 0;
+            u32 const nextAddr = (u32)__cvta_generic_to_shared(reinterpret_cast<u16*>(f.ct) + 2);
+            bool go = warp_encode_front<WIDE>(f, reinterpret_cast<const sym_t*>(src + (u64)b * g.blockSize), n, d, cap, msvReq, tlogReq, verdict, hSize, tl, nextAddr);
+            if (go) {
+                bool const usable = cap - hSize > 8;
+                if (!WIDE && (n <= 2 || !usable)) { go = false; verdict = 0; }
+                if (WIDE && !usable) { go = false; verdict = (u64)hSize >= (u64)(n - 1) * 2 ? 0 : hSize; }
+            }
+            if (lane == 0) {
+                sm.active[blk] = go; sm.hSize[blk] = hSize; sm.tl[blk] = tl;
+                if (!go) csizes[b] = verdict;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    u32 const iters = nBytes / 16;                                 // 16 source bytes = 8 chain steps
+    u32 const nGroups = iters / 4;                                 // GSTEPS = 32 steps
+    if (warp == 0) {
+        // ---- chain warp ----
+        u32 const blk = lane / CH, c = lane % CH;
+        bool const act = blk < (u32)EK && sm.active[blk < (u32)EK ? blk : 0];
+        u32 const bsafe = act ? blk : 0;
+        u32 const tl = act ? sm.tl[bsafe] : 5u;
+        u32 const size = 1u << tl;
+        const u32* const ct = sm.ct + bsafe * C::CT_WORDS + 1;
+        u32 const ttAddr = (u32)__cvta_generic_to_shared(ct + 1 + (size >> 1));
+        const uint4* const sp = reinterpret_cast<const uint4*>(src + (u64)(b0 + bsafe) * g.blockSize + g.blockSize) - 1;
+        u32* const ringLane = sm.ring + bsafe * C::RING_STRIDE + c;
+        u32 const selA = 0x4440u | (3 - c), selB = 0x4440u | (1 - c);  // byte pickers for even / odd steps of a register (bytes only)
+        u32 state = WIDE ? size : 0u;
+        // transforms of the 8 symbols this lane codes out of one 16-byte piece (descending addresses)
+        auto fetch = [&](const uint4& v, uint2 (&t)[8]) {
+            u32 const regs[4] = { v.w, v.z, v.y, v.x };
+            #pragma unroll
+            for (int q = 0; q < 8; q++) {
+                u32 const r = regs[q >> 1];
+                u32 const sym = WIDE ? ((q & 1) ? (r & 0xFFFFu) : (r >> 16)) : __byte_perm(r, 0, (q & 1) ? selB : selA);
+                t[q] = lds_v2(ttAddr + sym * 8);
+            }
+        };
+        uint4 q1 = make_uint4(0, 0, 0, 0), q2 = q1;              // pieces it+1, it+2 (in flight)
+        uint2 t[8], tn[8];
+        #pragma unroll
+        for (int q = 0; q < 8; q++) { t[q] = make_uint2(0, 0); tn[q] = t[q]; }
+        if (act) {
+            uint4 const q0 = __ldg(sp);
+            if (iters > 1) q1 = __ldg(sp - 1);
+            if (iters > 2) q2 = __ldg(sp - 2);
+            fetch(q0, tn);
+        }
+        for (u32 grp = 0; grp < nGroups; grp++) {
+            u32 const buf = grp & 1;
+            if (grp >= 2) bar_sync(3 + buf);
+            u32* rp = ringLane + buf * (EK * C::RING_STRIDE);
+            #pragma unroll 1
+            for (u32 i4 = 0; i4 < 4; i4++, rp += 8 * CH) {
+                u32 const it = grp * 4 + i4;
+                if (act) {
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) t[q] = tn[q];
+                    uint4 const nx = q1; q1 = q2;
+                    if (it + 3 < iters) q2 = __ldg(sp - (it + 3));
+                    if (it + 1 < iters) fetch(nx, tn);              // next piece's transforms, off the chain's critical path
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        u32 const x = t[q].x, y = t[q].y;           // { byte address of next[deltaFindState], maxBitsOut << 16 | minStatePlus }
+                        u32 rec;
+                        if (!WIDE && q == 0 && it == 0) {           // FSE_initCState2 (fse.h:503-512): no output
+                            u32 const dnb = (y & 0xFFFF0000u) - (y & 0xFFFFu);
+                            u32 const nb0 = (dnb + (1u << 15)) >> 16;
+                            u32 const v0 = (nb0 << 16) - dnb;
+                            state = lds_u16(x + 2 * (v0 >> nb0));
+                            rec = 0;
+                        } else {                                    // FSE_encodeSymbol (fse.h:514-521): nbBitsOut is maxBitsOut or one less
+                            u32 const maxb = y >> 16;
+                            bool const p = state >= (y & 0xFFFFu);
+                            u32 hi, lo;                              // both candidates at once (opaque to keep them off a select-the-amount chain)
+                            asm("shr.u32 %0, %1, %2;" : "=r"(hi) : "r"(state), "r"(maxb));
+                            asm("shr.u32 %0, %1, %2;" : "=r"(lo) : "r"(state), "r"(maxb - 1));
+                            rec = state + (y & 0xFFFF0000u) - (p ? 0u : 0x10000u);       // (state, nbBits): the emitter masks the value
+                            state = lds_u16(x + 2 * (p ? hi : lo));
+                        }
+                        rp[q * CH] = rec;
+                    }
+                }
+            }
+            __syncwarp();
+            bar_arrive(1 + buf);
+        }
+        {   // closing group: final states (fse_compress.c:608-609), end mark (bitstream.h:254-260)
+            u32 const buf = nGroups & 1;
+            if (nGroups >= 2) bar_sync(3 + buf);
+            u32* const rp = ringLane + buf * (EK * C::RING_STRIDE);
+            if (act) {
+                rp[0] = (state & (size - 1)) | (tl << 16);
+                rp[CH] = c == 0 ? (1u | (1u << 16)) : 0u;
+                for (u32 q = 2; q < (u32)GSTEPS; q++) rp[q * CH] = 0;
+            }
+            __syncwarp();
+            bar_arrive(1 + buf);
+        }
+    } else {
+        // ---- emitter warps: blocks e, e+7, e+14 ----
+        u32 const e = warp - 1;
+        u32* const words = sm.words + warp * 32;
+        u32 carry[3], carryBits[3], wpos[3], totalBits[3], mis[3], capWords[3]; u32* base32[3]; bool on[3];
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u32 const blk = e + 7 * k;
+            on[k] = blk < (u32)EK && sm.active[blk < (u32)EK ? blk : 0];
+            u32 const hs = on[k] ? sm.hSize[blk] : 0;
+            u8* const sbase = cbuf + (u64)(b0 + (on[k] ? blk : 0)) * g.slot + hs;
+            mis[k] = (u32)(reinterpret_cast<u64>(sbase) & 3);
+            base32[k] = reinterpret_cast<u32*>(sbase - mis[k]);
+            capWords[k] = (u32)((mis[k] + (cap - hs)) / 4);
+            carry[k] = 0; carryBits[k] = 8 * mis[k]; wpos[k] = 0; totalBits[k] = 0;
+        }
+        for (u32 grp = 0; grp <= nGroups; grp++) {
+            u32 const buf = grp & 1;
+            bar_sync(1 + buf);
+            #pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (!on[k]) continue;
+                const u32* const row = sm.ring + buf * (EK * C::RING_STRIDE) + (e + 7 * k) * C::RING_STRIDE;
+                u32 r0, r1 = 0;
+                if (WIDE) r0 = row[lane];
+                else { uint2 const rr = reinterpret_cast<const uint2*>(row)[lane]; r0 = rr.x; r1 = rr.y; }
+                emit_group<WIDE>(r0, r1, words, carry[k], carryBits[k], wpos[k], base32[k], capWords[k], mis[k], totalBits[k]);
+            }
+            __syncwarp();
+            if (grp + 2 <= nGroups) bar_arrive(3 + buf);
+        }
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (!on[k]) continue;
+            u32 const blk = e + 7 * k;
+            u32 const hSize = sm.hSize[blk];
+            u64 const scap = cap - hSize;
+            u64 streamBytes;
+            if ((u64)(totalBits[k] >> 3) >= scap - 8) streamBytes = 0;       // bitstream.h:190,258
+            else {
+                streamBytes = ((u64)totalBits[k] + 7) >> 3;
+                if (lane == 0 && carryBits[k] > 8 * mis[k] * (wpos[k] == 0)) {  // flush the partial last word byte by byte
+                    u32 const nby = (carryBits[k] + 7) / 8;
+                    u8* const p = reinterpret_cast<u8*>(base32[k] + wpos[k]);
+                    for (u32 i = (wpos[k] == 0 ? mis[k] : 0); i < nby; i++) p[i] = (u8)(carry[k] >> (8 * i));
+                }
+            }
+            u64 const totalOut = hSize + streamBytes;
+            u64 verdict;
+            if (!WIDE) verdict = (streamBytes == 0 || totalOut >= (u64)n - 1) ? 0 : totalOut;   // fse_compress.c:669,674
+            else verdict = totalOut >= (u64)(n - 1) * 2 ? 0 : totalOut;                         // fseU16.c:248
+            if (lane == 0) csizes[b0 + blk] = verdict;
+        }
+    }
+}
+
 }  // namespace fsek
 
 template <bool WIDE>
@@ -706,14 +1306,40 @@ static cudaError_t launch_dec(const BatchGeom& g, void* dst, const void* cbuf, c
 {
     if (g.nBlocks == 0) return cudaSuccess;
     size_t const smem = sizeof(fsek::DecWarp<WIDE>) * fsek::WARPS;
+    size_t const smemCta = sizeof(typename fsek::DecCta<WIDE>::Smem);
     static bool configured = false;
+    static bool legacy = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fsek::fse_decode_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fsek::fse_decode_cta_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCta);
+        if (e != cudaSuccess) return e;
+        const char* const v = getenv("FSEB200_DEC_LEGACY");         // tuning knob: the warp-per-block kernel
+        legacy = v && atoi(v) == 1;
         configured = true;
     }
-    unsigned const grid = (g.nBlocks + fsek::WARPS - 1) / fsek::WARPS;
-    fsek::fse_decode_kernel<WIDE><<<grid, fsek::THREADS, smem, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig);
+    if (legacy) {
+        unsigned const grid = (g.nBlocks + fsek::WARPS - 1) / fsek::WARPS;
+        fsek::fse_decode_kernel<WIDE><<<grid, fsek::THREADS, smem, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig);
+    } else {
+        unsigned const DK = fsek::DecCta<WIDE>::DK;
+        unsigned const grid = (g.nBlocks + DK - 1) / DK;
+        fsek::fse_decode_cta_kernel<WIDE><<<grid, fsek::DTHREADS, smemCta, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig);
+    }
+    return cudaGetLastError();
+}
+template <bool WIDE, int EK>
+static cudaError_t launch_enc_cta(const BatchGeom& g, u32 nFast, void* cbuf, u64* csizes, const void* src, unsigned msv, unsigned tlog, cudaStream_t stream)
+{
+    size_t const smemCta = sizeof(typename fsek::EncCta<WIDE, EK>::Smem);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t const e = cudaFuncSetAttribute(fsek::fse_encode_cta_kernel<WIDE, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCta);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    unsigned const grid = (nFast + EK - 1) / EK;
+    fsek::fse_encode_cta_kernel<WIDE, EK><<<grid, fsek::ETHREADS, smemCta, stream>>>(g, nFast, (u8*)cbuf, csizes, (const u8*)src, msv, tlog);
     return cudaGetLastError();
 }
 template <bool WIDE>
@@ -722,13 +1348,28 @@ static cudaError_t launch_enc(const BatchGeom& g, void* cbuf, u64* csizes, const
     if (g.nBlocks == 0) return cudaSuccess;
     size_t const smem = sizeof(fsek::EncWarp<WIDE>) * fsek::WARPS;
     static bool configured = false;
+    static int ek = 16;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fsek::fse_encode_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t const e = cudaFuncSetAttribute(fsek::fse_encode_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        const char* const v = getenv("FSEB200_ENC_EK");             // tuning knob: blocks per CTA of the chain-warp kernel (16 or 8)
+        if (v && atoi(v) == 8) ek = 8;
         configured = true;
     }
-    unsigned const grid = (g.nBlocks + fsek::WARPS - 1) / fsek::WARPS;
-    fsek::fse_encode_kernel<WIDE><<<grid, fsek::THREADS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog);
+    // full, aligned blocks go to the chain-warp kernel; a ragged last block or an odd geometry to the warp-per-block kernel
+    u64 const nFull = g.total / g.blockSize;
+    bool const fast = g.blockSize >= 64 && g.blockSize % 64 == 0 && (reinterpret_cast<u64>(src) & 15) == 0;
+    u32 const nFast = fast ? (u32)nFull : 0u;
+    if (nFast) {
+        cudaError_t const e = ek == 8 ? launch_enc_cta<WIDE, 8>(g, nFast, cbuf, csizes, src, msv, tlog, stream)
+                                      : launch_enc_cta<WIDE, 16>(g, nFast, cbuf, csizes, src, msv, tlog, stream);
+        if (e != cudaSuccess) return e;
+    }
+    if (nFast < g.nBlocks) {
+        unsigned const rest = g.nBlocks - nFast;
+        unsigned const grid = (rest + fsek::WARPS - 1) / fsek::WARPS;
+        fsek::fse_encode_kernel<WIDE><<<grid, fsek::THREADS, smem, stream>>>(g, nFast, (u8*)cbuf, csizes, (const u8*)src, msv, tlog);
+    }
     return cudaGetLastError();
 }
 
