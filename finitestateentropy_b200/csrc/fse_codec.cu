@@ -893,12 +893,12 @@ __device__ inline bool warp_encode_front(const EncFront<WIDE>& w, const typename
             u32 total = 0;
             for (u32 q = 0; q <= msv; q++) {
                 int const nn = w.norm[q];
-                if (chainBase) {                                    // chain form: { byte address of next[deltaFindState], maxBitsOut << 16 | minStatePlus }
-                    if (nn == 0) { tt[2 * q] = chainBase; tt[2 * q + 1] = (tl << 16) | size; continue; }
-                    if (nn == -1 || nn == 1) { tt[2 * q] = chainBase + 2 * (total - 1); tt[2 * q + 1] = (tl << 16) | size; total++; }
+                if (chainBase) {                                    // chain form: { byte address of next[deltaFindState], (maxBitsOut - 1) << 16 | minStatePlus }
+                    if (nn == 0) { tt[2 * q] = chainBase; tt[2 * q + 1] = ((tl - 1) << 16) | size; continue; }
+                    if (nn == -1 || nn == 1) { tt[2 * q] = chainBase + 2 * (total - 1); tt[2 * q + 1] = ((tl - 1) << 16) | size; total++; }
                     else {
                         u32 const maxOut = tl - hibit((u32)nn - 1);
-                        tt[2 * q] = chainBase + 2 * (total - (u32)nn); tt[2 * q + 1] = (maxOut << 16) | ((u32)nn << maxOut);
+                        tt[2 * q] = chainBase + 2 * (total - (u32)nn); tt[2 * q + 1] = ((maxOut - 1) << 16) | ((u32)nn << maxOut);
                         total += (u32)nn;
                     }
                     continue;
@@ -1196,33 +1196,34 @@ fse_encode_cta_kernel(BatchGeom g, u32 nFast, u8* __restrict__ cbuf, u64* __rest
             u32 const buf = grp & 1;
             if (grp >= 2) bar_sync(3 + buf);
             u32* rp = ringLane + buf * (EK * C::RING_STRIDE);
-            #pragma unroll 1
-            for (u32 i4 = 0; i4 < 4; i4++, rp += 8 * CH) {
+            #pragma unroll
+            for (u32 i4 = 0; i4 < 4; i4++, rp += 8 * CH) {          // fully unrolled: the two-deep queues rotate by renaming
                 u32 const it = grp * 4 + i4;
                 if (act) {
-                    #pragma unroll
-                    for (int q = 0; q < 8; q++) t[q] = tn[q];
-                    uint4 const nx = q1; q1 = q2;
-                    if (it + 3 < iters) q2 = __ldg(sp - (it + 3));
-                    if (it + 1 < iters) fetch(nx, tn);              // next piece's transforms, off the chain's critical path
+                    uint2 (&tc)[8] = (i4 & 1) ? t : tn;             // transforms of this piece (fetched one piece ago)
+                    uint2 (&tf)[8] = (i4 & 1) ? tn : t;             // ... and where the next piece's go
+                    uint4 const nx = (i4 & 1) ? q2 : q1;            // piece it+1
+                    if (it + 3 < iters) { if (i4 & 1) q2 = __ldg(sp - (it + 3)); else q1 = __ldg(sp - (it + 3)); }
+                    if (it + 1 < iters) fetch(nx, tf);              // off the chain's critical path
                     #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        u32 const x = t[q].x, y = t[q].y;           // { byte address of next[deltaFindState], maxBitsOut << 16 | minStatePlus }
+                        u32 const x = tc[q].x, y = tc[q].y;         // { byte address of next[deltaFindState], (maxBitsOut - 1) << 16 | minStatePlus }
+                        u32 const yhi = y & 0xFFFF0000u;
                         u32 rec;
-                        if (!WIDE && q == 0 && it == 0) {           // FSE_initCState2 (fse.h:503-512): no output
-                            u32 const dnb = (y & 0xFFFF0000u) - (y & 0xFFFFu);
+                        if (!WIDE && q == 0 && i4 == 0 && grp == 0) {   // FSE_initCState2 (fse.h:503-512): no output
+                            u32 const dnb = (yhi + 0x10000u) - (y & 0xFFFFu);
                             u32 const nb0 = (dnb + (1u << 15)) >> 16;
                             u32 const v0 = (nb0 << 16) - dnb;
                             state = lds_u16(x + 2 * (v0 >> nb0));
                             rec = 0;
-                        } else {                                    // FSE_encodeSymbol (fse.h:514-521): nbBitsOut is maxBitsOut or one less
-                            u32 const maxb = y >> 16;
-                            bool const p = state >= (y & 0xFFFFu);
-                            u32 hi, lo;                              // both candidates at once (opaque to keep them off a select-the-amount chain)
-                            asm("shr.u32 %0, %1, %2;" : "=r"(hi) : "r"(state), "r"(maxb));
-                            asm("shr.u32 %0, %1, %2;" : "=r"(lo) : "r"(state), "r"(maxb - 1));
-                            rec = state + (y & 0xFFFF0000u) - (p ? 0u : 0x10000u);       // (state, nbBits): the emitter masks the value
-                            state = lds_u16(x + 2 * (p ? hi : lo));
+                        } else {                                    // FSE_encodeSymbol (fse.h:514-521): nbBitsOut = maxBitsOut - (state < minStatePlus)
+                            u32 const r0 = state + yhi;             // state < 2^16: also state | (maxBitsOut-1) << 16
+                            bool const p = r0 >= y;                 // state >= minStatePlus
+                            u32 idx;
+                            asm("shr.u32 %0, %1, %2;" : "=r"(idx) : "r"(state), "r"(y >> 16));
+                            if (p) idx >>= 1;
+                            rec = p ? r0 + 0x10000u : r0;           // (state, nbBits): the emitter masks the value
+                            state = lds_u16(x + 2 * idx);
                         }
                         rp[q * CH] = rec;
                     }
