@@ -135,8 +135,41 @@ __device__ inline u64 cta_huf_build_ctable(u32* ctable, const u32* count, u32 ms
     return mb;
 }
 
+// 256 keys, element e = i * 32 + lane, sorted into DEcreasing order (bitonic network: shuffles for partners in other
+// lanes, plain compare-exchange for partners in the same lane).  Keys must be distinct.
+__device__ __forceinline__ void warp_sort256_desc(u32 (&key)[8], unsigned lane)
+{
+    #pragma unroll
+    for (u32 k = 2; k <= 256; k <<= 1) {
+        #pragma unroll
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                u32 const dj = j >> 5;
+                #pragma unroll
+                for (u32 i = 0; i < 8; i++) {
+                    if (i & dj) continue;
+                    u32 const e = i * 32;                          // lane bits do not matter for k >= 64
+                    bool const desc = (k == 256) || ((e & k) != 0) ;
+                    u32 const lo = min(key[i], key[i | dj]), hi = max(key[i], key[i | dj]);
+                    key[i] = desc ? hi : lo; key[i | dj] = desc ? lo : hi;
+                }
+            } else {
+                #pragma unroll
+                for (u32 i = 0; i < 8; i++) {
+                    u32 const e = i * 32 + lane;
+                    u32 const other = __shfl_xor_sync(0xFFFFFFFFu, key[i], j);
+                    bool const asc = (k == 256) ? false : ((e & k) == 0);
+                    bool const takeMin = ((e & j) == 0) == asc;
+                    key[i] = takeMin ? min(key[i], other) : max(key[i], other);
+                }
+            }
+        }
+    }
+}
+
 // Warp-cooperative variant (one warp builds one table; all operands in shared memory).
-// store: HNode[2*256+2]; lenOf: u8[256]; firstVal: u32[16].  Returns max code length or an error (warp-uniform).
+// store: HNode[2*256+2]; lenOf: u8[256]; firstVal: u32[16+16] (second half: running per-length counters).
+// Returns max code length or an error (warp-uniform).
 __device__ inline u64 warp_huf_build_ctable(u32* ctable, const u32* count, u32 msv, u32 maxBits,
                                             HNode* store, u8* lenOf, u32* firstVal)
 {
@@ -144,15 +177,19 @@ __device__ inline u64 warp_huf_build_ctable(u32* ctable, const u32* count, u32 m
     HNode* const nd = store + 1;
     if (!maxBits) maxBits = HUF_DEF_TLOG;
     if (msv > HUF_MAX_SV) return err(E_MSV_TOO_LARGE);
-    {   u64* const z = reinterpret_cast<u64*>(store);            // HNode is 8 bytes
-        for (u32 i = lane; i < 2 * 256 + 2; i += 32) z[i] = 0;
-    }
-    __syncwarp();
-    for (u32 s = lane; s <= msv; s += 32) {                      // rank by counting == stable sort by decreasing count
-        u32 const c = count[s];
-        u32 rank = 0;
-        for (u32 jj = 0; jj <= msv; jj++) { u32 const cj = count[jj]; rank += (cj > c) | ((cj == c) & (jj < s)); }
-        nd[rank].count = c; nd[rank].sym = (u8)s;
+    {   // HUF_sort (huf_compress.c:307-329): decreasing count, ties by increasing symbol == decreasing (count << 8 | 255 - symbol)
+        u32 key[8];
+        #pragma unroll
+        for (u32 i = 0; i < 8; i++) { u32 const s = i * 32 + lane; key[i] = ((s <= msv ? count[s] : 0u) << 8) | (255u - s); }
+        warp_sort256_desc(key, lane);
+        u64* const z = reinterpret_cast<u64*>(store);            // HNode is 8 bytes: {count, parent, sym, len}
+        #pragma unroll
+        for (u32 i = 0; i < 8; i++) {
+            HNode h; h.count = key[i] >> 8; h.parent = 0; h.sym = (u8)(255u - (key[i] & 0xFFu)); h.len = 0;
+            nd[i * 32 + lane] = h;
+        }
+        if (lane == 0) z[0] = 0;
+        for (u32 i = 257 + lane; i < 2 * 256 + 2; i += 32) z[i] = 0;
     }
     __syncwarp();
     u32 mb = 0; int last = 0;
@@ -164,11 +201,14 @@ __device__ inline u64 warp_huf_build_ctable(u32* ctable, const u32* count, u32 m
         fresh++; leaf -= 2;
         for (int n = fresh; n <= root; n++) nd[n].count = 1u << 30;
         nd[-1].count = 1u << 31;
+        u32 cl = nd[leaf].count, ci = nd[inner].count;           // heads of the two queues, kept in registers
         while (fresh <= root) {
-            int const a = (nd[leaf].count < nd[inner].count) ? leaf-- : inner++;
-            int const b = (nd[leaf].count < nd[inner].count) ? leaf-- : inner++;
-            nd[fresh].count = nd[a].count + nd[b].count;
-            nd[a].parent = nd[b].parent = (u16)fresh;
+            int a, b2; u32 ca, cb;
+            if (cl < ci) { a = leaf--; ca = cl; cl = nd[leaf].count; } else { a = inner++; ca = ci; ci = nd[inner].count; }
+            if (cl < ci) { b2 = leaf--; cb = cl; cl = nd[leaf].count; } else { b2 = inner++; cb = ci; ci = nd[inner].count; }
+            nd[fresh].count = ca + cb;
+            if (inner == fresh) ci = ca + cb;                    // the new node is the head of the inner queue
+            nd[a].parent = nd[b2].parent = (u16)fresh;
             fresh++;
         }
         nd[root].len = 0;
@@ -191,18 +231,23 @@ __device__ inline u64 warp_huf_build_ctable(u32* ctable, const u32* count, u32 m
     }
     mb = __shfl_sync(0xFFFFFFFFu, mb, 0);
     if (mb > HUF_MAX_TLOG) return err(E_GENERIC);
+    if (lane < 16) firstVal[16 + lane] = 0;
     __syncwarp();
     for (u32 s = lane; s <= msv; s += 32) lenOf[nd[s].sym] = nd[s].len;
     __syncwarp();
-    for (u32 s = lane; s < 256; s += 32) {
-        if (s <= msv) {
-            u32 const len = lenOf[s];
-            u32 before = 0;
-            for (u32 jj = 0; jj < s; jj++) before += (lenOf[jj] == len);
-            ctable[s] = ((firstVal[len] + before) & 0xFFFF) | (len << 16);
-        } else ctable[s] = 0;
+    // value = first value of the length + number of earlier symbols of that length (huf_compress.c:401-407), 32 symbols a round
+    u32* const seen = firstVal + 16;
+    for (u32 s0 = 0; s0 < 256; s0 += 32) {
+        u32 const s = s0 + lane;
+        u32 const len = s <= msv ? lenOf[s] : 31u;
+        u32 const peers = __match_any_sync(0xFFFFFFFFu, len);
+        u32 val = 0;
+        if (s <= msv) val = ((firstVal[len] + seen[len] + __popc(peers & ((1u << lane) - 1))) & 0xFFFF) | (len << 16);
+        __syncwarp();
+        if (s <= msv && (peers >> lane) == 1u) seen[len] += __popc(peers);
+        ctable[s] = val;
+        __syncwarp();
     }
-    __syncwarp();
     return mb;
 }
 

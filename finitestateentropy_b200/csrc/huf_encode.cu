@@ -52,7 +52,7 @@ struct PlanWarp {
     u32   count[256];
     HNode nodes[2 * 256 + 2];
     u32   ctable[256];
-    u32   firstVal[16];
+    u32   firstVal[32];         // first code value per length + running per-length counters
     u8    lenOf[256];
     u8    header[136];
     u32   wksp[384];
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(THREADS)
 huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u32* const ctab = reinterpret_cast<u32*>(smem_raw);             // 256 cells
-    u32* const image = ctab + 256;
+    uint2* const ctab = reinterpret_cast<uint2*>(smem_raw);         // 256 cells {code, nbBits}: one 8-byte load, no unpacking
+    u32* const image = reinterpret_cast<u32*>(ctab + 256);
     int const tid = threadIdx.x;
     unsigned const lane = tid & 31u; int const k = tid >> 5;
     u32 const b = blockIdx.x;
@@ -214,7 +214,9 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
     u32 const al = (u32)(reinterpret_cast<u64>(d) & 15);            // image byte i <-> d[i - al]
     u32 const imgWords = (al + total + 3) / 4 + 2;
 
-    ctab[tid] = P.ctable[tid]; ctab[tid + 128] = P.ctable[tid + 128];
+    {   u32 const c0 = P.ctable[tid], c1 = P.ctable[tid + 128];
+        ctab[tid] = make_uint2(c0 & 0xFFFFu, c0 >> 16); ctab[tid + 128] = make_uint2(c1 & 0xFFFFu, c1 >> 16);
+    }
     for (u32 i = tid; i < imgWords; i += THREADS) image[i] = 0;
     __syncthreads();
     {   u8* const img8 = reinterpret_cast<u8*>(image);
@@ -228,59 +230,94 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
         int const segEnd = (k < 3) ? (int)((k + 1) * seg) : (int)n;
         u32 const sTab = (u32)__cvta_generic_to_shared(ctab);
         u32 const sImg = (u32)__cvta_generic_to_shared(image);
-        u64 bitpos = 8ull * (al + P.streamOff[k]);
-        // the 4 symbols below hi-4*lane as one little-endian word (byte 3 = highest index = emitted first).  The raw
-        // word is kept as loaded: warps issue in order, so touching it here would stall on the load right away.
-        auto fetch = [&](int hi) -> u32 {
-            int const top = hi - 4 * (int)lane;                     // exclusive
-            u32 v = 0;
-            if (top - 4 >= segBeg && ((reinterpret_cast<u64>(s + top) & 3) == 0)) v = __ldg(reinterpret_cast<const u32*>(s + top - 4));
-            else if (top > segBeg) {
-                #pragma unroll
-                for (int j = 0; j < 4; j++) { int const i = top - 1 - j; if (i >= segBeg) v |= (u32)s[i] << (8 * (3 - j)); }
-            }
-            return v;
-        };
-        auto lds32 = [&](u32 a) -> u32 { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+        u32 bitpos = 8u * (al + P.streamOff[k]);                    // < 2^19
+        auto lds64 = [&](u32 a) -> uint2 { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; };
         auto red_or = [&](u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); };
-        // groups of 128 symbols, walked from the end of the segment; loads run 4 groups ahead of the packing
-        constexpr int PF = 4;
-        u32 pre[PF];
-        #pragma unroll
-        for (int i = 0; i < PF; i++) pre[i] = (segEnd - 128 * i > segBeg) ? fetch(segEnd - 128 * i) : 0u;
-        for (int hi0 = segEnd; hi0 > segBeg; hi0 -= 128 * PF) {
+        auto red_or_nz = [&](u32 a, u32 v) {                        // predicated, not branched
+            asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0], %1; }" :: "r"(a), "r"(v) : "memory");
+        };
+        // lane's bits (a0 | a1 << 32, `held` of them) go to bit offset (bitpos + exclusive prefix) of the image
+        auto place = [&](u32 a0, u32 a1, u32 held) -> u32 {
+            u32 incl = held;
             #pragma unroll
-            for (int i = 0; i < PF; i++) {
-                int const hi = hi0 - 128 * i;
-                if (hi <= segBeg) break;                            // warp-uniform
-                u32 const cur = pre[i];
-                if (hi - 128 * PF > segBeg) pre[i] = fetch(hi - 128 * PF);
-                int const top = hi - 4 * (int)lane;
-                int const nValid = top - segBeg;                    // symbols available to this lane (>= 4 for all but the last group)
+            for (int dd = 1; dd < 32; dd <<= 1)                     // shfl.up's own predicate says whether a source lane exists
+                asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(incl) : "r"(dd));
+            u32 const sum = __shfl_sync(FULL, incl, 31);
+            u32 const at = bitpos + (incl - held);
+            u32 const wa = sImg + 4 * (at >> 5);
+            u32 const sh = at & 31;
+            u32 const w0 = a0 << sh, w1 = __funnelshift_l(a0, a1, sh), w2 = __funnelshift_l(a1, 0, sh);
+            red_or_nz(wa, w0);
+            red_or_nz(wa + 4, w1);
+            red_or_nz(wa + 8, w2);
+            return sum;
+        };
+        constexpr int PF = 4;
+        // ---- full groups of 128 symbols on word-aligned data: lane l codes the 4 symbols of one 32-bit word, highest byte first ----
+        bool const wordAligned = ((reinterpret_cast<u64>(s) + (u64)segEnd) & 3) == 0;
+        int const nFull = wordAligned ? (segEnd - segBeg) / 128 : 0;
+        {
+            const u32* gp = reinterpret_cast<const u32*>(s + segEnd) - 1 - lane;            // group j: word gp[-32 j]
+            auto group = [&](u32 o0, u32 o1, u32 o2, u32 o3) {      // table offsets of the 4 symbols, emission order
+                uint2 const e0 = lds64(sTab + o0), e1 = lds64(sTab + o1), e2 = lds64(sTab + o2), e3 = lds64(sTab + o3);
+                u32 const p01 = e0.x | (e1.x << e0.y), l01 = e0.y + e1.y;           // <= 22 bits
+                u32 const p23 = e2.x | (e3.x << e2.y), l23 = e2.y + e3.y;
+                u32 const a0 = p01 | (p23 << l01), a1 = __funnelshift_l(p23, 0, l01);
+                bitpos += place(a0, a1, l01 + l23);
+            };
+            // rounds of PF groups: a raw word is unpacked one round after its load was issued, and it is dead (unpacked into
+            // table offsets) before the next load is issued into its register -- warps issue in order, so no instruction
+            // may touch a register with a load in flight
+            int const rounds = nFull / PF;
+            u32 bufA[PF], bufB[PF];                                 // two register sets, used alternately: nothing is ever rotated
+            #pragma unroll
+            for (int i = 0; i < PF; i++) { bufA[i] = rounds > 0 ? __ldg(gp - 32 * i) : 0u; bufB[i] = 0u; }
+            auto round = [&](u32 (&X)[PF], u32 (&Y)[PF], int r) {   // code the groups held in X, request the next round into Y
+                gp -= 32 * PF;
+                bool const more = r + 1 < rounds;
+                #pragma unroll
+                for (int i = 0; i < PF; i++) {
+                    u32 const cur = X[i];
+                    if (more) Y[i] = __ldg(gp - 32 * i);
+                    group(8 * (cur >> 24), 8 * __byte_perm(cur, 0, 0x4442), 8 * __byte_perm(cur, 0, 0x4441), 8 * (cur & 0xFFu));
+                }
+            };
+            int r = 0;
+            #pragma unroll 1
+            for (; r + 1 < rounds; r += 2) { round(bufA, bufB, r); round(bufB, bufA, r + 1); }
+            if (r < rounds) round(bufA, bufB, r);
+            for (int j = rounds * PF; j < nFull; j++) {             // < PF groups left
+                u32 const cur = __ldg(reinterpret_cast<const u32*>(s + segEnd) - 1 - lane - 32 * j);
+                group(8 * (cur >> 24), 8 * __byte_perm(cur, 0, 0x4442), 8 * __byte_perm(cur, 0, 0x4441), 8 * (cur & 0xFFu));
+            }
+        }
+        // ---- what is left (a partial group, or everything when the segment end is not word aligned) ----
+        {
+            int const rest = segEnd - 128 * nFull;
+            auto fetch = [&](int hi) -> u32 {                       // the 4 symbols below hi-4*lane as one little-endian word
+                int const top = hi - 4 * (int)lane;                 // exclusive
+                u32 v = 0;
+                if (top - 4 >= segBeg && ((reinterpret_cast<u64>(s + top) & 3) == 0)) v = __ldg(reinterpret_cast<const u32*>(s + top - 4));
+                else if (top > segBeg) {
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++) { int const i = top - 1 - j; if (i >= segBeg) v |= (u32)s[i] << (8 * (3 - j)); }
+                }
+                return v;
+            };
+            #pragma unroll 1
+            for (int hi = rest; hi > segBeg; hi -= 128) {
+                u32 const cur = fetch(hi);
+                int const nValid = hi - 4 * (int)lane - segBeg;     // symbols available to this lane
                 u64 acc = 0; u32 held = 0;                          // up to 48 bits
                 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    u32 const e = lds32(sTab + 4 * ((cur >> (8 * (3 - j))) & 0xFF));
-                    if (j < nValid) { acc |= (u64)(e & 0xFFFF) << held; held += e >> 16; }
+                    uint2 const e = lds64(sTab + 8 * ((cur >> (8 * (3 - j))) & 0xFF));
+                    if (j < nValid) { acc |= (u64)e.x << held; held += e.y; }
                 }
-                u32 const a0 = (u32)acc, a1 = (u32)(acc >> 32);
-                u32 incl = held;
-                #pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) { u32 const t = __shfl_up_sync(FULL, incl, dd); if (lane >= (unsigned)dd) incl += t; }
-                u32 const sum = __shfl_sync(FULL, incl, 31);
-                if (held) {
-                    u64 const at = bitpos + (incl - held);
-                    u32 const wa = sImg + 4 * (u32)(at >> 5);
-                    u32 const sh = (u32)(at & 31);
-                    u32 const w0 = a0 << sh, w1 = __funnelshift_l(a0, a1, sh), w2 = __funnelshift_l(a1, 0, sh);
-                    if (w0) red_or(wa, w0);
-                    if (w1) red_or(wa + 4, w1);
-                    if (w2) red_or(wa + 8, w2);
-                }
-                bitpos += sum;
+                bitpos += place((u32)acc, (u32)(acc >> 32), held);
             }
         }
-        if (lane == 0) red_or(sImg + 4 * (u32)(bitpos >> 5), 1u << (bitpos & 31));      // end mark (bitstream.h:256)
+        if (lane == 0) red_or(sImg + 4 * (bitpos >> 5), 1u << (bitpos & 31));          // end mark (bitstream.h:256)
     }
     __syncthreads();
     // ---- copy out (HBM write) ----
@@ -319,7 +356,7 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
         unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
         hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans);
     }
-    {   size_t const smem = 256 * sizeof(u32) + (size_t)g.blockSize + 64 + 16 + 16;           // code table + image (accepted blocks are < n bytes)
+    {   size_t const smem = 256 * sizeof(uint2) + (size_t)g.blockSize + 64 + 16 + 16;           // code table + image (accepted blocks are < n bytes)
         static size_t configured = 0;
         if (smem > configured) {
             e = cudaFuncSetAttribute(hufe::huf_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
