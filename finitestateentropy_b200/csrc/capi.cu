@@ -129,7 +129,7 @@ size_t one_block_decompress(dec_fn fn, void* dst, size_t dstBytes, const void* c
 // caller then downloads what it needs from the scratch.
 struct Micro {
     Workspace& w; unsigned char* buf; u64* ret; std::unique_lock<std::mutex> lock;
-    Micro() : w(ws()), lock(w.mu) { buf = (unsigned char*)w.get(3, 256 * 1024); ret = (u64*)w.get(2, 2 * sizeof(u64)); }
+    explicit Micro(size_t bytes = 256 * 1024) : w(ws()), lock(w.mu) { buf = (unsigned char*)w.get(3, bytes < 256 * 1024 ? 256 * 1024 : bytes); ret = (u64*)w.get(2, 2 * sizeof(u64)); }
     void up(size_t off, const void* p, size_t n) { if (n) CK(cudaMemcpyAsync(buf + off, p, n, cudaMemcpyHostToDevice, w.stream)); }
     void down(void* p, size_t off, size_t n) { if (n) { CK(cudaMemcpyAsync(p, buf + off, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); } }
     u64 run(int op, u64 a0 = 0, u64 a1 = 0, u64 a2 = 0, u64 a3 = 0)
@@ -418,6 +418,69 @@ FSEB_API size_t HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSi
     unsigned const tl = (hdr >> 16) & 0xFF;
     m.down(DTable, 16384, sizeof(unsigned) + ((size_t)1 << tl) * 2);
     return (size_t)r;
+}
+
+// ---- payload coding with a caller-supplied table (the tables are ABI: fse.h:295-296,483-486,565-575 ; huf.h:136-149) ----
+namespace {
+constexpr size_t MICRO_MAX = (size_t)1 << 24;                           // single-call payloads above 16 MiB are refused (use the batch tier)
+size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
+}
+FSEB_API size_t FSE_compress_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* ct)   // lib/fse.h:222
+{
+    unsigned const tl = ct[0] & 0xFFFF, msv = ct[0] >> 16;
+    if (tl > FSE_MAX_TLOG || tl < 1) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (msv > FSE_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    if (srcSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const cap = dstSize < 2 * srcSize + 64 ? dstSize : 2 * srcSize + 64;     // <= 12 bits per symbol: more room can never be used
+    size_t const ctBytes = (1 + ((size_t)1 << (tl - 1)) + 2 * ((size_t)msv + 1)) * sizeof(unsigned);
+    size_t const inOff = 16384, outOff = inOff + al16(srcSize + 16);
+    Micro m(outOff + cap + 64);
+    m.up(0, ct, ctBytes); m.up(inOff, src, srcSize);
+    u64 const r = m.run(MOP_FSE_ENCODE_CT, srcSize, cap, inOff, outOff);
+    if (!is_err(r) && r) m.down(dst, outOff, (size_t)r);
+    return (size_t)r;
+}
+FSEB_API size_t FSE_decompress_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* dt)   // lib/fse.h:247
+{
+    unsigned const tl = dt[0] & 0xFFFF;
+    if (tl > FSE_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (cSrcSize > MICRO_MAX || maxDstSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const inOff = 32768, outOff = inOff + al16(cSrcSize + 16);
+    Micro m(outOff + maxDstSize + 64);
+    m.up(0, dt, (1 + ((size_t)1 << tl)) * sizeof(unsigned)); m.up(inOff, cSrc, cSrcSize);
+    u64 const r = m.run(MOP_FSE_DECODE_DT, cSrcSize, maxDstSize, inOff, outOff);
+    if (!is_err(r) && r) m.down(dst, outOff, (size_t)r);
+    return (size_t)r;
+}
+FSEB_API size_t HUF_compress4X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable)   // lib/huf.h:191
+{
+    if (srcSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const cap = dstSize < 2 * srcSize + 64 ? dstSize : 2 * srcSize + 64;
+    size_t const inOff = 4096, outOff = inOff + al16(srcSize + 16);
+    Micro m(outOff + 5 * al16(cap) + 64);
+    m.up(0, CTable, 256 * sizeof(unsigned)); m.up(inOff, src, srcSize);
+    u64 const r = m.run(MOP_HUF_ENCODE4X_CT, srcSize, cap, inOff, outOff);
+    if (!is_err(r) && r) m.down(dst, outOff, (size_t)r);
+    return (size_t)r;
+}
+FSEB_API size_t HUF_decompress4X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)   // lib/huf.h:277
+{
+    unsigned const type = (DTable[0] >> 8) & 0xFF, tl = (DTable[0] >> 16) & 0xFF;
+    if (type != 0) return (size_t)err(E_GENERIC);                                   // huf_decompress.c:434
+    if (tl > HUF_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (cSrcSize > MICRO_MAX || maxDstSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const inOff = 16384, outOff = inOff + al16(cSrcSize + 16);
+    Micro m(outOff + maxDstSize + 64);
+    m.up(0, DTable, sizeof(unsigned) + ((size_t)1 << tl) * 2); m.up(inOff, cSrc, cSrcSize);
+    u64 const r = m.run(MOP_HUF_DECODE4X1_DT, cSrcSize, maxDstSize, inOff, outOff);
+    if (!is_err(r)) m.down(dst, outOff, maxDstSize);
+    return (size_t)r;
+}
+FSEB_API size_t HUF_decompress4X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)    // lib/huf.h:203
+{
+    // huf_decompress.c:980-997 dispatches on DTableDesc.tableType; double-symbol (X2) images are not produced by this library
+    // (HUF_readDTableX2 is not exported), so only single-symbol tables can reach here
+    return HUF_decompress4X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);
 }
 
 // ================================================================================================

@@ -79,10 +79,9 @@ __device__ __forceinline__ void warp_hist_range(u32* cnt, const u8* s, u32 begin
                 u32 const wd[4] = { x[h].x, x[h].y, x[h].z, x[h].w };
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    u32 const y = wd[k];
-                    u32 const b0 = y & 0xFF, b1 = (y >> 8) & 0xFF, b2 = (y >> 16) & 0xFF, b3 = y >> 24;
-                    if ((b0 == b1) & (b1 == b2) & (b2 == b3)) atomicAdd(&cnt[b0], 4u);
-                    else { atomicAdd(&cnt[b0], 1u); atomicAdd(&cnt[b1], 1u); atomicAdd(&cnt[b2], 1u); atomicAdd(&cnt[b3], 1u); }
+                    u32 const y = wd[k];                             // one extract + one address + one shared atomic per byte
+                    atomicAdd(&cnt[y & 0xFF], 1u); atomicAdd(&cnt[__byte_perm(y, 0, 0x4441)], 1u);
+                    atomicAdd(&cnt[__byte_perm(y, 0, 0x4442)], 1u); atomicAdd(&cnt[y >> 24], 1u);
                 }
             }
         }

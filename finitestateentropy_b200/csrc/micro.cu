@@ -115,6 +115,92 @@ __global__ void __launch_bounds__(256) micro_kernel(int op, MicroArgs A, u8* buf
             *ret = h;
         }
         break; }
+    // ---- payload coding with a caller-supplied table image (the *_usingCTable / *_usingDTable entry points): table @0,
+    //      input @a2 (a0 bytes), output @a3 (capacity a1).  One lane per stream; these serve single calls, not throughput.
+    case MOP_FSE_ENCODE_CT: {      // FSE_compress_usingCTable (fse_compress.c:554-623)
+        if (tid == 0) *ret = d_fse_encode_serial(buf + A.a[3], A.a[1], buf + A.a[2], A.a[0], (const u32*)buf);
+        break; }
+    case MOP_FSE_DECODE_DT: {      // FSE_decompress_usingDTable (fse_decompress.c:178-252)
+        if (tid == 0) *ret = d_fse_decode_serial(buf + A.a[3], A.a[1], buf + A.a[2], A.a[0], (const u32*)buf);
+        break; }
+    case MOP_HUF_ENCODE4X_CT: {    // HUF_compress4X_usingCTable (huf_compress.c:552-603): lane k codes segment k, lane 0 assembles
+        __shared__ u64 s_len[4];
+        const u32* const ct = (const u32*)buf;
+        const u8* const in = buf + A.a[2]; u8* const out = buf + A.a[3];
+        u64 const n = A.a[0], cap = A.a[1];
+        u64 const seg = (n + 3) / 4;
+        bool const refuse = cap < 6 + 1 + 1 + 1 + 8 || n < 12;                       // :564-565
+        u8* const stage = buf + A.a[3] + ((cap + 15) & ~15ull);                     // 4 private areas of `cap` bytes behind the output
+        if (tid < 4 && !refuse) {
+            u64 const beg = seg * tid, end = tid < 3 ? seg * (tid + 1) : n;
+            BitSink sk; sink_open(sk, stage + tid * ((cap + 15) & ~15ull), cap);     // capacity is judged by lane 0 with the real remaining room
+            for (u64 i = end; i-- > beg;) { u32 const e = ct[in[i]]; sink_put(sk, e & 0xFFFF, e >> 16); }
+            sink_put(sk, 1, 1);                                                      // end mark
+            s_len[tid] = sk.nbits;
+            if (sk.held) { if (sk.nbytes < cap) sk.out[sk.nbytes] = (u8)sk.acc; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (refuse) { *ret = 0; break; }
+            u64 op = 6; u64 r = 0; bool ok = true;
+            for (int k = 0; k < 4 && ok; k++) {
+                u64 const room = cap - op;                                           // BIT_initCStream / closeCStream rules (bitstream.h:183-260)
+                u64 const bits = s_len[k], bytes = (bits + 7) >> 3;
+                if (room <= 8 || (bits >> 3) >= room - 8) { ok = false; break; }
+                const u8* const sp = stage + k * ((cap + 15) & ~15ull);
+                for (u64 i = 0; i < bytes; i++) out[op + i] = sp[i];
+                if (k < 3) { out[2 * k] = (u8)bytes; out[2 * k + 1] = (u8)(bytes >> 8); }
+                op += bytes;
+            }
+            r = ok ? op : 0;
+            *ret = r;
+        }
+        break; }
+    case MOP_HUF_DECODE4X1_DT: {   // HUF_decompress4X1_usingDTable (huf_decompress.c:262-354): lane k decodes stream k into segment k
+        __shared__ u64 s_init[4]; __shared__ u32 s_done[4];
+        const u32* const dtab = (const u32*)buf;
+        const u16* const cells = (const u16*)(dtab + 1);                             // HUF_DEltX1 { byte, nbBits }
+        u32 const dtLog = (dtab[0] >> 16) & 0xFF;
+        const u8* const c = buf + A.a[2]; u8* const out = buf + A.a[3];
+        u64 const cs = A.a[0], n = A.a[1];
+        bool bad = cs < 10;                                                          // :268
+        u64 l1 = 0, l2 = 0, l3 = 0, l4 = 0;
+        if (!bad) {
+            l1 = c[0] | ((u64)c[1] << 8); l2 = c[2] | ((u64)c[3] << 8); l3 = c[4] | ((u64)c[5] << 8);
+            if (l1 + l2 + l3 + 6 > cs) bad = true; else l4 = cs - (l1 + l2 + l3 + 6);   // the reference would read out of bounds here
+        }
+        u64 const seg = (n + 3) / 4;
+        if (!bad && 3 * seg > n) bad = true;                                         // dstSize < 6: the reference writes out of bounds (documented deviation)
+        if (tid < 4) {
+            u64 ie = 0; u32 done = 0;
+            if (!bad) {
+                u64 const lens[4] = { l1, l2, l3, l4 };
+                u64 off = 6; for (int k = 0; k < tid; k++) off += lens[k];
+                long long p = (long long)(seg * tid); long long const pe = tid < 3 ? (long long)(seg * (tid + 1)) : (long long)n;
+                BitSrc b;
+                ie = bs_open(b, c + off, lens[tid]);
+                if (!is_err(ie)) {
+                    ie = 0;
+                    auto sym = [&]() { u32 const cell = cells[bs_peek_fast(b, dtLog)]; b.used += cell >> 8; out[p++] = (u8)cell; };
+                    while ((bs_refill(b) == SRC_MORE) & (p < pe - 3)) { sym(); sym(); sym(); sym(); }   // HUF_decodeStreamX1 :214-237
+                    while (p < pe) sym();
+                    done = bs_exhausted(b) ? 1u : 0u;                                // :348-349
+                }
+            }
+            s_init[tid] = ie; s_done[tid] = done;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            u64 r = n;
+            if (bad) r = err(E_CORRUPT);
+            else {
+                bool initFailed = false;
+                for (int k = 0; k < 4; k++) if (is_err(s_init[k])) { r = s_init[k]; initFailed = true; break; }   // CHECK_F in stream order (:297-300)
+                if (!initFailed && !(s_done[0] & s_done[1] & s_done[2] & s_done[3])) r = err(E_CORRUPT);
+            }
+            *ret = r;
+        }
+        break; }
     default: if (tid == 0) *ret = err(E_GENERIC);
     }
 }

@@ -131,6 +131,15 @@ size_t      HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSize);
 unsigned    HUF_selectDecoder(size_t dstSize, size_t cSrcSize);
 size_t      HUF_decompress4X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
 size_t      HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
+/* Payload coding with a caller-built table image (lib/fse.h:222,247 ; lib/huf.h:191,203,277).  The images are the
+ * reference's own ABI layouts (FSE_CTable fse.h:295,483-486 ; FSE_DTable fse.h:296,565-575 ; HUF_CElt huf_compress.c:106-109 ;
+ * HUF_DTable single-symbol huf_decompress.c:101,116), e.g. as produced by FSE_buildCTable / FSE_buildDTable /
+ * HUF_buildCTable / HUF_readDTableX1 above or by the CPU library.  Single synchronous calls on host buffers, <= 16 MiB. */
+size_t      FSE_compress_usingCTable(void* dst, size_t dstCapacity, const void* src, size_t srcSize, const unsigned* ct);
+size_t      FSE_decompress_usingDTable(void* dst, size_t dstCapacity, const void* cSrc, size_t cSrcSize, const unsigned* dt);
+size_t      HUF_compress4X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable);
+size_t      HUF_decompress4X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
+size_t      HUF_decompress4X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
 /* lib/fseU16.h:75-79 */
 size_t      FSE_compressU16(void* dst, size_t dstCapacity, const unsigned short* src, size_t srcSize,
                             unsigned maxSymbolValue, unsigned tableLog);

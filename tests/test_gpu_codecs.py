@@ -249,6 +249,40 @@ def test_table_level_api_images():
         assert g_hdt(ptr(dA), ptr(ha), wa) == lib.HUF_readDTableX1(ptr(dB), ptr(hb), wb) == wa
         ncell = 1 + ((1 << tA.value) + 1) // 2
         assert np.array_equal(dA[:ncell], dB[:ncell])
+        # payload coding with the caller's tables: FSE_compress_usingCTable / FSE_decompress_usingDTable /
+        # HUF_compress4X_usingCTable / HUF_decompress4X[1]_usingDTable (same images on both sides)
+        g_euc = sig("FSE_compress_usingCTable", C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+        g_dud = sig("FSE_decompress_usingDTable", C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+        g_huc = sig("HUF_compress4X_usingCTable", C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+        g_hud = sig("HUF_decompress4X_usingDTable", C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+        for r_ in ("FSE_compress_usingCTable", "FSE_decompress_usingDTable", "HUF_compress4X_usingCTable", "HUF_decompress4X_usingDTable"):
+            f = getattr(lib, r_); f.restype = C.c_size_t; f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        for cap in (n + 600, max(16, n // 3)):
+            oa = np.zeros(cap + 16, np.uint8); ob = np.zeros(cap + 16, np.uint8)
+            ea = g_euc(ptr(oa), cap, ptr(d), n, ptr(ctb)); eb = lib.FSE_compress_usingCTable(ptr(ob), cap, ptr(d), n, ptr(ctb))
+            assert ea == eb and bytes(oa[:ea]) == bytes(ob[:eb])
+            if ea and cap > n:
+                ra_ = np.zeros(n + 8, np.uint8); rb_ = np.zeros(n + 8, np.uint8)
+                for dcap in (n, n - 1, n + 5):
+                    da = g_dud(ptr(ra_), dcap, ptr(oa), ea, ptr(dtb)); db = lib.FSE_decompress_usingDTable(ptr(rb_), dcap, ptr(ob), eb, ptr(dtb))
+                    assert da == db
+                    if not is_error(da):
+                        assert bytes(ra_[:da]) == bytes(rb_[:db])
+                bad = oa[:ea].copy(); bad[int(rng.integers(0, ea))] ^= 1 << int(rng.integers(0, 8))
+                da = g_dud(ptr(ra_), n, ptr(bad), ea, ptr(dtb)); db = lib.FSE_decompress_usingDTable(ptr(rb_), n, ptr(bad), ea, ptr(dtb))
+                assert da == db
+            ha2 = np.zeros(cap + 16, np.uint8); hb2 = np.zeros(cap + 16, np.uint8)
+            ea = g_huc(ptr(ha2), cap, ptr(d), n, ptr(tb)); eb = lib.HUF_compress4X_usingCTable(ptr(hb2), cap, ptr(d), n, ptr(tb))
+            assert ea == eb and bytes(ha2[:ea]) == bytes(hb2[:eb])
+            if ea and n >= 6:
+                ra_ = np.zeros(n + 8, np.uint8); rb_ = np.zeros(n + 8, np.uint8)
+                da = g_hud(ptr(ra_), n, ptr(ha2), ea, ptr(dB)); db = lib.HUF_decompress4X_usingDTable(ptr(rb_), n, ptr(hb2), eb, ptr(dB))
+                assert da == db == n and bytes(ra_[:n]) == bytes(rb_[:n]) == bytes(d[:n])
+                bad = ha2[:ea].copy(); bad[int(rng.integers(6, ea))] ^= 1 << int(rng.integers(0, 8))      # past the jump table: the CPU library trusts it
+                da = g_hud(ptr(ra_), n, ptr(bad), ea, ptr(dB)); db = lib.HUF_decompress4X_usingDTable(ptr(rb_), n, ptr(bad), ea, ptr(dB))
+                assert is_error(da) == is_error(db)
+                if is_error(da):
+                    assert da == db
 
 
 @pytest.mark.parametrize("codec,p,mib", [("huf", 0.14, 64), ("fse", 0.80, 16)])
