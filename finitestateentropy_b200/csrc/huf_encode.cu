@@ -235,28 +235,78 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
         auto red_or_nz = [&](u32 a, u32 v) {                        // predicated, not branched
             asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0], %1; }" :: "r"(a), "r"(v) : "memory");
         };
-        // lane's bits (a0 | a1 << 32, `held` of them) go to bit offset (bitpos + exclusive prefix) of the image
-        auto place = [&](u32 a0, u32 a1, u32 held) -> u32 {
+        // warp scan of the lanes' bit counts: exclusive prefix in `excl`, returns the warp total
+        auto scan = [&](u32 held, u32& excl) -> u32 {
             u32 incl = held;
             #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1)                     // shfl.up's own predicate says whether a source lane exists
                 asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(incl) : "r"(dd));
-            u32 const sum = __shfl_sync(FULL, incl, 31);
-            u32 const at = bitpos + (incl - held);
+            excl = incl - held;
+            return __shfl_sync(FULL, incl, 31);
+        };
+        // ORs up to 64 bits (a0 | a1 << 32) into the image at bit offset `at`
+        auto put = [&](u32 at, u32 a0, u32 a1) {
             u32 const wa = sImg + 4 * (at >> 5);
             u32 const sh = at & 31;
-            u32 const w0 = a0 << sh, w1 = __funnelshift_l(a0, a1, sh), w2 = __funnelshift_l(a1, 0, sh);
-            red_or_nz(wa, w0);
-            red_or_nz(wa + 4, w1);
-            red_or_nz(wa + 8, w2);
+            red_or_nz(wa, a0 << sh);
+            red_or_nz(wa + 4, __funnelshift_l(a0, a1, sh));
+            red_or_nz(wa + 8, __funnelshift_l(a1, 0, sh));
+        };
+        auto place = [&](u32 a0, u32 a1, u32 held) -> u32 {         // lane's `held` bits go to bitpos + exclusive prefix
+            u32 excl; u32 const sum = scan(held, excl);
+            put(bitpos + excl, a0, a1);
             return sum;
         };
         constexpr int PF = 4;
-        // ---- full groups of 128 symbols on word-aligned data: lane l codes the 4 symbols of one 32-bit word, highest byte first ----
-        bool const wordAligned = ((reinterpret_cast<u64>(s) + (u64)segEnd) & 3) == 0;
-        int const nFull = wordAligned ? (segEnd - segBeg) / 128 : 0;
+        int hiCur = segEnd;                                         // symbols [segBeg, hiCur) are still to be coded
+        // ---- groups of 256 symbols on 8-byte-aligned data: lane l codes the 8 symbols of one 64-bit piece, highest byte first.
+        //      One scan serves 8 symbols; the two 4-symbol halves (<= 44 bits each) are placed separately. ----
         {
-            const u32* gp = reinterpret_cast<const u32*>(s + segEnd) - 1 - lane;            // group j: word gp[-32 j]
+            bool const al8 = ((reinterpret_cast<u64>(s) + (u64)segEnd) & 7) == 0;
+            int const nBig = al8 ? (segEnd - segBeg) / 256 : 0;
+            const uint2* gq = reinterpret_cast<const uint2*>(s + segEnd) - 1 - lane;         // group j: piece gq[-32 j]
+            auto half = [&](u32 w, u32& a0, u32& a1) -> u32 {        // 4 symbols of one word -> up to 44 bits
+                uint2 const e0 = lds64(sTab + 8 * (w >> 24)), e1 = lds64(sTab + 8 * __byte_perm(w, 0, 0x4442));
+                uint2 const e2 = lds64(sTab + 8 * __byte_perm(w, 0, 0x4441)), e3 = lds64(sTab + 8 * (w & 0xFFu));
+                u32 const p01 = e0.x | (e1.x << e0.y), l01 = e0.y + e1.y;
+                u32 const p23 = e2.x | (e3.x << e2.y), l23 = e2.y + e3.y;
+                a0 = p01 | (p23 << l01); a1 = __funnelshift_l(p23, 0, l01);
+                return l01 + l23;
+            };
+            auto big = [&](uint2 cur) {
+                u32 x0, x1, y0, y1;
+                u32 const lx = half(cur.y, x0, x1), ly = half(cur.x, y0, y1);       // .y holds the higher addresses: emitted first
+                u32 excl; u32 const sum = scan(lx + ly, excl);
+                put(bitpos + excl, x0, x1);
+                put(bitpos + excl + lx, y0, y1);
+                bitpos += sum;
+            };
+            constexpr int PB = 2;                                   // pieces in flight per register set (2 x 256 B per warp)
+            int const rounds = nBig / PB;
+            uint2 bufA[PB], bufB[PB];
+            #pragma unroll
+            for (int i = 0; i < PB; i++) { bufA[i] = rounds > 0 ? __ldg(gq - 32 * i) : make_uint2(0, 0); bufB[i] = make_uint2(0, 0); }
+            auto round = [&](uint2 (&X)[PB], uint2 (&Y)[PB], int r) {
+                gq -= 32 * PB;
+                bool const more = r + 1 < rounds;
+                #pragma unroll
+                for (int i = 0; i < PB; i++) {
+                    uint2 const cur = X[i];
+                    if (more) Y[i] = __ldg(gq - 32 * i);
+                    big(cur);
+                }
+            };
+            int r = 0;
+            #pragma unroll 1
+            for (; r + 1 < rounds; r += 2) { round(bufA, bufB, r); round(bufB, bufA, r + 1); }
+            if (r < rounds) round(bufA, bufB, r);
+            hiCur -= 256 * rounds * PB;
+        }
+        // ---- full groups of 128 symbols on word-aligned data: lane l codes the 4 symbols of one 32-bit word, highest byte first ----
+        bool const wordAligned = ((reinterpret_cast<u64>(s) + (u64)hiCur) & 3) == 0;
+        int const nFull = wordAligned ? (hiCur - segBeg) / 128 : 0;
+        {
+            const u32* gp = reinterpret_cast<const u32*>(s + hiCur) - 1 - lane;             // group j: word gp[-32 j]
             auto group = [&](u32 o0, u32 o1, u32 o2, u32 o3) {      // table offsets of the 4 symbols, emission order
                 uint2 const e0 = lds64(sTab + o0), e1 = lds64(sTab + o1), e2 = lds64(sTab + o2), e3 = lds64(sTab + o3);
                 u32 const p01 = e0.x | (e1.x << e0.y), l01 = e0.y + e1.y;           // <= 22 bits
@@ -286,13 +336,13 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             for (; r + 1 < rounds; r += 2) { round(bufA, bufB, r); round(bufB, bufA, r + 1); }
             if (r < rounds) round(bufA, bufB, r);
             for (int j = rounds * PF; j < nFull; j++) {             // < PF groups left
-                u32 const cur = __ldg(reinterpret_cast<const u32*>(s + segEnd) - 1 - lane - 32 * j);
+                u32 const cur = __ldg(reinterpret_cast<const u32*>(s + hiCur) - 1 - lane - 32 * j);
                 group(8 * (cur >> 24), 8 * __byte_perm(cur, 0, 0x4442), 8 * __byte_perm(cur, 0, 0x4441), 8 * (cur & 0xFFu));
             }
         }
         // ---- what is left (a partial group, or everything when the segment end is not word aligned) ----
         {
-            int const rest = segEnd - 128 * nFull;
+            int const rest = hiCur - 128 * nFull;
             auto fetch = [&](int hi) -> u32 {                       // the 4 symbols below hi-4*lane as one little-endian word
                 int const top = hi - 4 * (int)lane;                 // exclusive
                 u32 v = 0;
