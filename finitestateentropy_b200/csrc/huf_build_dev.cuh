@@ -298,4 +298,117 @@ __device__ inline u64 d_huf_write_ctable(u8* out, u64 cap, const u32* ctable, un
     return ((msv + 1) / 2) + 1;
 }
 
+// ---- warp-cooperative HUF_writeCTable (huf_compress.c:114-147) with HUF_compressWeights (:63-103) ----
+// Same results as the one-lane versions above.  The weight histogram, the two tANS chains (lane 0: even indices /
+// state 1, lane 1: odd indices / state 2 -- fse_compress.c:572-606) and the bit packing (prefix scan of the emitted
+// (value, nbBits) records) use the warp; the 13-symbol normalisation, NCount and CTable stay on lane 0.
+// out: shared memory, 4-byte aligned, at least `cap` (<= 136) bytes.  wksp: >= 360 u32.  All lanes call; result uniform.
+__device__ inline u64 warp_huf_compress_weights(u8* out, u64 cap, const u8* w, u32 n, u32* wksp)
+{
+    unsigned const lane = threadIdx.x & 31u;
+    unsigned* const count = wksp;                     // 13
+    short* const norm = (short*)(wksp + 16);          // 13 shorts
+    u32* const ct = wksp + 24;                        // 1 + 32 + 2*13 = 59
+    u16* const cellSym = (u16*)(wksp + 84);           // 64 u16
+    u32* const start = wksp + 116;                    // 15
+    u16* const rec = (u16*)(wksp + 224);              // 256 records (value | nbBits << 8)
+    if (n <= 1) return 0;
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) atomicAdd(&count[w[i]], 1u);
+    __syncwarp();
+    unsigned msv = HUF_MAX_TLOG, best = 0;
+    while (!count[msv]) msv--;
+    for (unsigned s = 0; s <= msv; s++) best = count[s] > best ? count[s] : best;
+    if (best == n) return 1;
+    if (best == 1) return 0;
+    unsigned const tl = d_optimal_tablelog(6, n, msv, 2);
+    u64 r = 0;
+    if (lane == 0) {
+        r = d_normalize(norm, tl, count, n, msv);
+        if (!is_err(r)) r = d_write_ncount(out, cap, norm, msv, tl);
+        if (!is_err(r)) d_build_ctable_serial(ct, norm, msv, tl, cellSym, start);
+    }
+    r = __shfl_sync(0xFFFFFFFFu, r, 0);
+    if (is_err(r)) return r;
+    u32 const o = (u32)r;
+    __syncwarp();
+    if (n <= 2) return 0;                             // fse_compress.c:563
+    u64 const scap = cap - o;
+    if (scap <= 8) return 0;                          // BIT_initCStream refuses (bitstream.h:190)
+    CtView const c = ct_view(ct);
+    u32 state = 0;
+    if (lane < 2) {                                   // the two interleaved chains
+        bool seeded = false;
+        int const first = (int)(((n - 1) & 1u) == lane ? n - 1 : n - 2);
+        for (int i = first; i >= 0; i -= 2) {
+            u32 const sym = w[i];
+            if (!seeded) { state = enc_seed(c, sym); seeded = true; rec[i] = 0; }
+            else {
+                u32 const nb = (state + c.tt[2 * sym + 1]) >> 16;
+                rec[i] = (u16)((state & ((1u << nb) - 1)) | (nb << 8));
+                state = c.next[(state >> nb) + c.tt[2 * sym]];
+            }
+        }
+    }
+    u32 const s0 = __shfl_sync(0xFFFFFFFFu, state, 0), s1 = __shfl_sync(0xFFFFFFFFu, state, 1);
+    // zero the stream area, then OR every record at its bit offset (aligned words of the shared buffer)
+    for (u32 i = o + lane; i < (u32)cap; i += 32) out[i] = 0;
+    __syncwarp();
+    u64 const a0 = reinterpret_cast<u64>(out + o);
+    u32* const words = reinterpret_cast<u32*>(a0 & ~3ull);
+    u32 const limitWords = (u32)(((a0 & 3) + scap + 3) / 4);
+    u32 running = 8 * (u32)(a0 & 3);
+    u32 const bit0 = running;
+    u32 const R = n + 3;
+    for (u32 k0 = 0; k0 < R; k0 += 32) {
+        u32 const k = k0 + lane;
+        u32 e = 0;
+        if (k < n) e = rec[n - 1 - k];
+        else if (k == n) e = (s1 & ((1u << tl) - 1)) | (tl << 8);        // flush state 2, then state 1, then the end mark
+        else if (k == n + 1) e = (s0 & ((1u << tl) - 1)) | (tl << 8);
+        else if (k == n + 2) e = 1u | (1u << 8);
+        u32 const nb = e >> 8, val = e & 0xFF;
+        u32 incl = nb;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 const t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (unsigned)d) incl += t; }
+        u32 const sum = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (nb) {
+            u32 const off = running + incl - nb;
+            u32 const wi = off >> 5, sh = off & 31;
+            if (wi < limitWords) atomicOr(&words[wi], val << sh);
+            if (sh + nb > 32 && wi + 1 < limitWords) atomicOr(&words[wi + 1], val >> (32 - sh));
+        }
+        running += sum;
+    }
+    __syncwarp();
+    u32 const totalBits = running - bit0;
+    if ((u64)(totalBits >> 3) >= scap - 8) return 0;  // bitstream.h:246,258
+    return (u64)o + ((totalBits + 7) >> 3);
+}
+
+__device__ inline u64 warp_huf_write_ctable(u8* out, u64 cap, const u32* ctable, unsigned msv, unsigned huffLog, u32* wksp)
+{
+    unsigned const lane = threadIdx.x & 31u;
+    u8* const weight = (u8*)(wksp + 160);             // 256 bytes
+    if (msv > HUF_MAX_SV) return err(E_MSV_TOO_LARGE);
+    for (unsigned n = lane; n < msv; n += 32) {
+        unsigned const len = (ctable[n] >> 16) & 0xFF;
+        weight[n] = (u8)(len ? huffLog + 1 - len : 0);
+    }
+    __syncwarp();
+    {   u64 const h = warp_huf_compress_weights(out + 1, cap - 1, weight, msv, wksp);
+        if (is_err(h)) return h;
+        if ((h > 1) & (h < msv / 2)) { if (lane == 0) out[0] = (u8)h; __syncwarp(); return h + 1; }
+    }
+    if (msv > 128) return err(E_GENERIC);
+    if (((msv + 1) / 2) + 1 > cap) return err(E_DST_TOO_SMALL);
+    __syncwarp();
+    if (lane == 0) { out[0] = (u8)(128 + (msv - 1)); weight[msv] = 0; }
+    __syncwarp();
+    for (unsigned n = 2 * lane; n < msv; n += 64) out[(n / 2) + 1] = (u8)((weight[n] << 4) + weight[n + 1]);
+    __syncwarp();
+    return ((msv + 1) / 2) + 1;
+}
+
 }  // namespace fseb

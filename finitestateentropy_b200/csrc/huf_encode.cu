@@ -23,6 +23,7 @@
 //      histograms of the plan kernel.  (An earlier version gave each thread a contiguous run of
 //      symbols staged in shared memory: runs are 128 bytes apart, i.e. all 32 lanes of a warp in the
 //      same bank -- 525M bank conflicts per 256 MiB, short-scoreboard 38 stalls per issue.)
+#include <cstdlib>
 #include "common.cuh"
 #include "fse_dev.cuh"
 #include "sink_dev.cuh"
@@ -54,7 +55,7 @@ struct PlanWarp {
     u32   ctable[256];
     u32   firstVal[32];         // first code value per length + running per-length counters
     u8    lenOf[256];
-    u8    header[136];
+    alignas(4) u8 header[136];
     u32   wksp[384];
 };
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ void warp_hist_range(u32* cnt, const u8* s, u32 begin
 
 __global__ void __launch_bounds__(32 * PLAN_WARPS)
 huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
-                unsigned msvReq, unsigned tlogReq, Plan* __restrict__ plans)
+                unsigned msvReq, unsigned tlogReq, Plan* __restrict__ plans, int serialHeader)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PlanWarp& w = reinterpret_cast<PlanWarp*>(smem_raw)[threadIdx.x >> 5];
@@ -147,8 +148,8 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     }
     // ---- tree header (huf_compress.c:703-716) ----
     u64 hs = 0;
-    if (lane == 0) hs = d_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, w.wksp);
-    hs = __shfl_sync(FULL, hs, 0);
+    if (serialHeader) { if (lane == 0) hs = d_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, w.wksp); hs = __shfl_sync(FULL, hs, 0); }
+    else hs = warp_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, w.wksp);
     if (is_err(hs)) FSEB_FINAL(hs);
     if (hs + 12 >= n) FSEB_FINAL(0);
     u64 const capLeft = cap - hs;
@@ -395,6 +396,8 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
     hufe::Plan* plans = nullptr;
     e = cudaMallocAsync((void**)&plans, sizeof(hufe::Plan) * (size_t)g.nBlocks, stream);     // stream-ordered scratch
     if (e != cudaSuccess) return e;
+    static int serialHeader = -1;
+    if (serialHeader < 0) { const char* const v = getenv("FSEB200_HUF_SERIAL_HEADER"); serialHeader = (v && atoi(v) == 1) ? 1 : 0; }   // tuning knob
     {   size_t const smem = sizeof(hufe::PlanWarp) * hufe::PLAN_WARPS;
         static bool configured = false;
         if (!configured) {
@@ -403,7 +406,7 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
             configured = true;
         }
         unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
-        hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans);
+        hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans, serialHeader);
     }
     {   size_t const smem = 256 * sizeof(uint2) + (size_t)g.blockSize + 64 + 16 + 16;           // code table + image (accepted blocks are < n bytes)
         static size_t configured = 0;
