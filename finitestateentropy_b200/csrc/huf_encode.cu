@@ -24,6 +24,8 @@
 //      symbols staged in shared memory: runs are 128 bytes apart, i.e. all 32 lanes of a warp in the
 //      same bank -- 525M bank conflicts per 256 MiB, short-scoreboard 38 stalls per issue.)
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "fse_dev.cuh"
 #include "sink_dev.cuh"
@@ -394,7 +396,27 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
     if (g.nBlocks == 0) return cudaSuccess;
     cudaError_t e;
     hufe::Plan* plans = nullptr;
-    e = cudaMallocAsync((void**)&plans, sizeof(hufe::Plan) * (size_t)g.nBlocks, stream);     // stream-ordered scratch
+    // Plan scratch (1.25 KB per block).  Default: one grow-only buffer per stream, reused by successive calls (stream order
+    // makes that safe; a different stream gets its own buffer).  FSEB200_SCRATCH_ASYNC=1 switches to cudaMallocAsync/FreeAsync.
+    static int asyncScratch = -1;
+    if (asyncScratch < 0) { const char* const v = getenv("FSEB200_SCRATCH_ASYNC"); asyncScratch = (v && atoi(v) == 1) ? 1 : 0; }
+    size_t const need = sizeof(hufe::Plan) * (size_t)g.nBlocks;
+    if (asyncScratch) e = cudaMallocAsync((void**)&plans, need, stream);
+    else {
+        struct Slot { cudaStream_t s; void* p; size_t cap; };
+        static std::mutex mu; static std::vector<Slot> slots;
+        std::lock_guard<std::mutex> lock(mu);
+        Slot* hit = nullptr;
+        for (auto& sl : slots) if (sl.s == stream) { hit = &sl; break; }
+        if (!hit) { slots.push_back(Slot{ stream, nullptr, 0 }); hit = &slots.back(); }
+        e = cudaSuccess;
+        if (hit->cap < need) {
+            if (hit->p) { cudaStreamSynchronize(stream); cudaFree(hit->p); hit->p = nullptr; hit->cap = 0; }
+            e = cudaMalloc(&hit->p, need);
+            if (e == cudaSuccess) hit->cap = need;
+        }
+        plans = (hufe::Plan*)hit->p;
+    }
     if (e != cudaSuccess) return e;
     static int serialHeader = -1;
     if (serialHeader < 0) { const char* const v = getenv("FSEB200_HUF_SERIAL_HEADER"); serialHeader = (v && atoi(v) == 1) ? 1 : 0; }   // tuning knob
@@ -418,7 +440,7 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
         hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, smem, stream>>>(g, (u8*)cbuf, (const u8*)src, plans);
     }
     e = cudaGetLastError();
-    cudaError_t const e2 = cudaFreeAsync(plans, stream);
+    cudaError_t const e2 = asyncScratch ? cudaFreeAsync(plans, stream) : cudaSuccess;
     return e != cudaSuccess ? e : e2;
 }
 
