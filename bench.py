@@ -233,6 +233,7 @@ def run_b200(a):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's own banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = fb.lib()
     for nm, args in (("FSEB200_probagen", [C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p]),
