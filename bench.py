@@ -210,7 +210,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(1e3 * (tc + td) / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic (probagen restatement, seed 1)",
-            "config": {"workload": "probagen P=%.0f%% %d MiB, %s encode+decode, 32 KB blocks, (255,12)" % (a.p * 100, n >> 20, a.codec.upper()),
+            "config": {"workload": "probagen P=%.0f%% %d MiB per GPU, %s encode+decode, 32 KB blocks, (255,12)" % (a.p * 100, n >> 20, "Huff0 4X" if a.codec == "huf" else "FSE"),
                        "block_size": BLOCK, "slot": SLOT, "host_threads": threads},
             "encode_gbs": round(n * a.steps / tc / 1e9, 3), "decode_gbs": round(n * a.steps / td / 1e9, 3),
             "compressed_ratio": round(float(cs.astype(np.float64).sum()) / n, 5), "wall_s": round(wall, 2),
