@@ -641,7 +641,20 @@ fse_decode_cta_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ 
                 windowed = true;
             }
             u64 const p0 = p; u32 const k0 = k;
-#define FSEB_NORM() do { bool const adv_ = k >= 32; if (adv_) { w0 = w1; w1 = w2; w2 = q; q = ldw(p); p -= 4; k -= 32; } } while (0)
+// window advance, fully predicated: no branch, and the only instruction that reads q is the move that retires the word
+// requested one advance earlier (warps issue in order: anything else touching q would wait for the load in flight)
+#define FSEB_NORM() asm volatile("{\n\t.reg .pred a, g;\n\t" \
+                "setp.ge.u32 a, %4, 32;\n\t" \
+                "setp.ge.u64 g, %5, %6;\n\t" \
+                "and.pred g, g, a;\n\t" \
+                "@a mov.b32 %0, %1;\n\t" \
+                "@a mov.b32 %1, %2;\n\t" \
+                "@a mov.b32 %2, %3;\n\t" \
+                "@a mov.b32 %3, 0;\n\t" \
+                "@g ld.global.nc.u32 %3, [%5];\n\t" \
+                "@a add.u64 %5, %5, -4;\n\t" \
+                "@a add.u32 %4, %4, -32;\n\t}" \
+                : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(q), "+r"(k), "+l"(p) : "l"(lowest) : "memory")
 #define FSEB_PSTEP(ST, SYM, FIRST) do { \
                 u32 cell_, nb_, base_; \
                 if (WIDE) { cell_ = lds_u32(tabAddr + 4 * ST); SYM = cell_ >> 20; nb_ = (cell_ >> 16) & 0xF; base_ = cell_ & 0xFFFF; } \
