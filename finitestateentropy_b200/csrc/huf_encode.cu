@@ -192,18 +192,17 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
 // A stream is the concatenation, last symbol first, of the codes.  The warp walks its segment from the
 // end in groups of 128 symbols: lane l takes the 4 symbols just below hi-4l (coalesced global read,
 // nothing staged), concatenates their codes (<= 48 bits), a warp scan of the lengths gives its bit
-// offset, and it ORs the bits into the shared-memory image of the compressed block at the final
-// position of the stream (known from the plan).  Then the image is copied out with aligned 16-byte
-// stores (image and destination share their alignment mod 16).
+// offset, and it ORs the bits into a circular shared-memory window of the stream (aligned 32-bit words of the
+// destination, whose position is known from the plan); completed words are written out 32 at a time.
 // ---------------------------------------------------------------------------------------------
 constexpr int THREADS = 128;
 
 __global__ void __launch_bounds__(THREADS)
 huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2* const ctab = reinterpret_cast<uint2*>(smem_raw);         // 256 cells {code, nbBits}: one 8-byte load, no unpacking
-    u32* const image = reinterpret_cast<u32*>(ctab + 256);
+    constexpr u32 W = 256;                                          // words of stream window per warp (a group adds <= 88, < 32 wait for the next flush)
+    __shared__ uint2 ctab[256];                                     // cells {code, nbBits}: one 8-byte load, no unpacking
+    __shared__ u32 winAll[4 * W];
     int const tid = threadIdx.x;
     unsigned const lane = tid & 31u; int const k = tid >> 5;
     u32 const b = blockIdx.x;
@@ -213,26 +212,31 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
     const u8* const s = src + (u64)b * g.blockSize;
     u8* const d = cbuf + (u64)b * g.slot;
     u32 const hSize = P.hSize, total = P.total;
-    u32 const al = (u32)(reinterpret_cast<u64>(d) & 15);            // image byte i <-> d[i - al]
-    u32 const imgWords = (al + total + 3) / 4 + 2;
 
     {   u32 const c0 = P.ctable[tid], c1 = P.ctable[tid + 128];
         ctab[tid] = make_uint2(c0 & 0xFFFFu, c0 >> 16); ctab[tid + 128] = make_uint2(c1 & 0xFFFFu, c1 >> 16);
     }
-    for (u32 i = tid; i < imgWords; i += THREADS) image[i] = 0;
-    __syncthreads();
-    {   u8* const img8 = reinterpret_cast<u8*>(image);
-        for (u32 i = tid; i < hSize; i += THREADS) img8[al + i] = P.header[i];
-        if (tid < 3) { u32 const v = P.streamBytes[tid]; img8[al + hSize + 2 * tid] = (u8)v; img8[al + hSize + 2 * tid + 1] = (u8)(v >> 8); }
-    }
+    for (u32 i = tid; i < 4 * W; i += THREADS) winAll[i] = 0;
+    // tree header and jump table straight to the block (byte stores: the word they end in is shared with stream 1)
+    for (u32 i = tid; i < hSize; i += THREADS) d[i] = P.header[i];
+    if (tid < 3) { u32 const v = P.streamBytes[tid]; d[hSize + 2 * tid] = (u8)v; d[hSize + 2 * tid + 1] = (u8)(v >> 8); }
     __syncthreads();
     {
         u32 const seg = (n + 3) / 4;
         int const segBeg = (int)(k * seg);
         int const segEnd = (k < 3) ? (int)((k + 1) * seg) : (int)n;
         u32 const sTab = (u32)__cvta_generic_to_shared(ctab);
-        u32 const sImg = (u32)__cvta_generic_to_shared(image);
-        u32 bitpos = 8u * (al + P.streamOff[k]);                    // < 2^19
+        // The stream is built in a circular window of aligned 32-bit words of the destination and flushed as it grows, so a
+        // CTA needs 6 KB of shared memory instead of an image of the whole block (occupancy: 10+ CTAs per SM instead of 6).
+        u32* const win = winAll + k * W;
+        u32 const sWin = (u32)__cvta_generic_to_shared(win);
+        u8* const gstart = d + P.streamOff[k];
+        u32 const a0 = (u32)(reinterpret_cast<u64>(gstart) & 3);
+        u32* const gw = reinterpret_cast<u32*>(gstart - a0);        // word j of the window <-> gw[j]
+        u32 const sBytes = (k < 3) ? P.streamBytes[k] : total - P.streamOff[3];
+        u32 const endByte = a0 + sBytes;                            // stream occupies local bytes [a0, endByte)
+        u32 bitpos = 8u * a0;
+        u32 flushed = 0;                                            // words already written out
         auto lds64 = [&](u32 a) -> uint2 { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; };
         auto red_or = [&](u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); };
         auto red_or_nz = [&](u32 a, u32 v) {                        // predicated, not branched
@@ -247,13 +251,27 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             excl = incl - held;
             return __shfl_sync(FULL, incl, 31);
         };
-        // ORs up to 64 bits (a0 | a1 << 32) into the image at bit offset `at`
-        auto put = [&](u32 at, u32 a0, u32 a1) {
-            u32 const wa = sImg + 4 * (at >> 5);
-            u32 const sh = at & 31;
-            red_or_nz(wa, a0 << sh);
-            red_or_nz(wa + 4, __funnelshift_l(a0, a1, sh));
-            red_or_nz(wa + 8, __funnelshift_l(a1, 0, sh));
+        // ORs up to 64 bits (a0 | a1 << 32) into the window at bit offset `at`
+        auto put = [&](u32 at, u32 x0, u32 x1) {
+            u32 const j = at >> 5, sh = at & 31;
+            red_or_nz(sWin + 4 * (j & (W - 1)), x0 << sh);
+            red_or_nz(sWin + 4 * ((j + 1) & (W - 1)), __funnelshift_l(x0, x1, sh));
+            red_or_nz(sWin + 4 * ((j + 2) & (W - 1)), __funnelshift_l(x1, 0, sh));
+        };
+        // writes out window words [flushed, upTo) that are final; word 0 and the last word may be shared with a neighbour
+        auto store_word = [&](u32 j, u32 v) {
+            u32 const lo = 4 * j, hi = 4 * j + 4;
+            if (lo >= a0 && hi <= endByte) gw[j] = v;
+            else { u8* const pb = reinterpret_cast<u8*>(gw + j); for (u32 t = 0; t < 4; t++) if (lo + t >= a0 && lo + t < endByte) pb[t] = (u8)(v >> (8 * t)); }
+        };
+        auto flush = [&](bool all) {
+            __syncwarp();
+            u32 const upTo = all ? (endByte + 3) / 4 : (bitpos >> 5);
+            while (all ? flushed < upTo : flushed + 32 <= upTo) {
+                u32 const j = flushed + lane;
+                if (j < upTo) { u32 const v = win[j & (W - 1)]; win[j & (W - 1)] = 0; store_word(j, v); }
+                flushed += 32;
+            }
         };
         auto place = [&](u32 a0, u32 a1, u32 held) -> u32 {         // lane's `held` bits go to bitpos + exclusive prefix
             u32 excl; u32 const sum = scan(held, excl);
@@ -283,6 +301,7 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                 put(bitpos + excl, x0, x1);
                 put(bitpos + excl + lx, y0, y1);
                 bitpos += sum;
+                flush(false);
             };
             constexpr int PB = 2;                                   // pieces in flight per register set (2 x 256 B per warp)
             int const rounds = nBig / PB;
@@ -316,6 +335,7 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                 u32 const p23 = e2.x | (e3.x << e2.y), l23 = e2.y + e3.y;
                 u32 const a0 = p01 | (p23 << l01), a1 = __funnelshift_l(p23, 0, l01);
                 bitpos += place(a0, a1, l01 + l23);
+                flush(false);
             };
             // rounds of PF groups: a raw word is unpacked one round after its load was issued, and it is dead (unpacked into
             // table offsets) before the next load is issued into its register -- warps issue in order, so no instruction
@@ -367,24 +387,12 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                     if (j < nValid) { acc |= (u64)e.x << held; held += e.y; }
                 }
                 bitpos += place((u32)acc, (u32)(acc >> 32), held);
+                flush(false);
             }
         }
-        if (lane == 0) red_or(sImg + 4 * (bitpos >> 5), 1u << (bitpos & 31));          // end mark (bitstream.h:256)
-    }
-    __syncthreads();
-    // ---- copy out (HBM write) ----
-    {   const u8* const img8 = reinterpret_cast<const u8*>(image);
-        u32 const first16 = (al + 15) & ~15u;
-        u32 const endOff = al + total;
-        if (first16 >= endOff) { for (u32 i = al + tid; i < endOff; i += THREADS) d[i - al] = img8[i]; }
-        else {
-            for (u32 i = al + tid; i < first16; i += THREADS) d[i - al] = img8[i];
-            u32 const nvec = (endOff - first16) / 16;
-            const uint4* const iv = reinterpret_cast<const uint4*>(img8 + first16);
-            uint4* const ov = reinterpret_cast<uint4*>(d + (first16 - al));
-            for (u32 i = tid; i < nvec; i += THREADS) ov[i] = iv[i];
-            for (u32 i = first16 + nvec * 16 + tid; i < endOff; i += THREADS) d[i - al] = img8[i];
-        }
+        if (lane == 0) red_or(sWin + 4 * ((bitpos >> 5) & (W - 1)), 1u << (bitpos & 31));    // end mark (bitstream.h:256)
+        bitpos += 1;
+        flush(true);                                                // the rest, byte-exact at both ends
     }
 }
 
@@ -430,15 +438,7 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
         unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
         hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans, serialHeader);
     }
-    {   size_t const smem = 256 * sizeof(uint2) + (size_t)g.blockSize + 64 + 16 + 16;           // code table + image (accepted blocks are < n bytes)
-        static size_t configured = 0;
-        if (smem > configured) {
-            e = cudaFuncSetAttribute(hufe::huf_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
-        hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, smem, stream>>>(g, (u8*)cbuf, (const u8*)src, plans);
-    }
+    hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, 0, stream>>>(g, (u8*)cbuf, (const u8*)src, plans);
     e = cudaGetLastError();
     cudaError_t const e2 = asyncScratch ? cudaFreeAsync(plans, stream) : cudaSuccess;
     return e != cudaSuccess ? e : e2;
