@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--p", type=float, default=0.14)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sg", action="store_true", help="skip the separate scatter/decode/gather line at N > 1")
     return ap.parse_args()
 
 
@@ -233,8 +234,14 @@ def run_b200(a):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's own banner must not land on stdout next to the JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout while the first communicator comes up: stdout must carry the JSON line only
+        sys.stdout.flush(); saved_fd = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            C.CDLL(None).fflush(None)                              # NCCL writes through libc's buffered stdout
+            sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
     L = fb.lib()
     for nm, args in (("FSEB200_probagen", [C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p]),
                      ("FSEB200_compress_host", [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint]),
@@ -349,6 +356,42 @@ def run_b200(a):
                "note": "PCIe-bound: each call moves 1 GiB one way (about 19.5 ms at the measured 55 GB/s)"}
         del h_src, h_c, h_out
 
+    # ---- BASELINE configs[3] shape, reported separately: the root scatters the compressed shards over NVLink, every
+    #      rank decodes its shard, the root gathers the decoded shards.  Bounded by the root's link, not by the codec. ----
+    sg = None
+    if dist is not None and world > 1 and not a.no_sg and a.codec == "huf":
+        parts_c = [torch.empty_like(cbuf) for _ in range(world)] if rank == 0 else None
+        parts_s = [torch.empty_like(cs) for _ in range(world)] if rank == 0 else None
+        dist.gather(cbuf, parts_c, dst=0); dist.gather(cs, parts_s, dst=0)           # setup: the root now holds every shard, compressed
+        parts_o = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        rc = torch.empty_like(cbuf); rs = torch.empty_like(cs)
+
+        def sg_step():
+            dist.scatter(rc, parts_c, src=0); dist.scatter(rs, parts_s, src=0)
+            dec(rc, rs, n, BLOCK, SLOT, out=out, results=res, orig=None)
+            dist.gather(out, parts_o, dst=0)
+        sg_step()
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        ks = 3
+        g0.record()
+        for _ in range(ks):
+            sg_step()
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        okt = torch.tensor([1 if torch.equal(out, src) else 0], dtype=torch.int32, device=dev)
+        if rank == 0:
+            okt &= int(torch.equal(parts_o[0], src))
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok_sg = bool(int(okt.cpu()[0]))
+        ms = float(tg.cpu()[0]) / ks
+        sg = {"what": "root scatters compressed Huff0 shards (full slots), all ranks decode, root gathers decoded shards; NCCL send/recv over NVLink",
+              "decode_gbs_incl_transfers": round(world * n / (ms * 1e-3) / 1e9, 2), "ms_per_step": round(ms, 3), "steps": ks,
+              "bytes_scattered": (world - 1) * int(cbuf.numel()), "bytes_gathered": (world - 1) * n, "roundtrip_ok": ok_sg}
+        del parts_c, parts_o, rc
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -393,7 +436,7 @@ def run_b200(a):
             "encode_gbs_per_gpu": round(n / (enc_ms * 1e-3) / 1e9, 2), "decode_gbs_per_gpu": round(n / (dec_ms * 1e-3) / 1e9, 2),
             "per_gpu": round(value / world, 3), "compressed_ratio": round(csum / n, 5),
             "bit_exact": bit_exact, "roundtrip_ok": ok_rt,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (3 if a.codec == "huf" else 2) * a.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": sg, "gpu_launches": (3 if a.codec == "huf" else 2) * a.steps,
             "clocks": sampler.summary(wall0, wall1) if sampler else None}
     print(json.dumps(line))
     if dist is not None:
