@@ -93,6 +93,41 @@ __device__ __forceinline__ void warp_hist_range(u32* cnt, const u8* s, u32 begin
     for (u32 k = i + lane; k < end; k += 32) atomicAdd(&cnt[s[k]], 1u);
 }
 
+// All four per-segment histograms of an aligned block whose segments are whole 2 KB batches (the 32 KB case): one
+// software pipeline over the block, the next batch's four 16-byte loads are in flight while the current one is counted,
+// on two alternating register sets (nothing touches a register with a load in flight).
+__device__ __forceinline__ void warp_hist4_pipelined(u32 (*count4)[256], const u8* s, u32 n, u32 seg, unsigned lane)
+{
+    const uint4* const gv = reinterpret_cast<const uint4*>(s) + lane;
+    u32 const B = n / 2048, perSeg = seg / 2048;
+    auto load = [&](uint4 (&x)[4], u32 b) {
+        #pragma unroll
+        for (int h = 0; h < 4; h++) x[h] = __ldg(gv + b * 128 + 32 * h);
+    };
+    auto count = [&](const uint4 (&x)[4], u32 b) {
+        u32* const cnt = count4[b / perSeg];
+        #pragma unroll
+        for (int h = 0; h < 4; h++) {
+            u32 const wd[4] = { x[h].x, x[h].y, x[h].z, x[h].w };
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 const y = wd[k];                                 // one extract + one address + one shared atomic per byte
+                atomicAdd(&cnt[y & 0xFF], 1u); atomicAdd(&cnt[__byte_perm(y, 0, 0x4441)], 1u);
+                atomicAdd(&cnt[__byte_perm(y, 0, 0x4442)], 1u); atomicAdd(&cnt[y >> 24], 1u);
+            }
+        }
+    };
+    uint4 xa[4], xb[4];
+    load(xa, 0);
+    #pragma unroll 1
+    for (u32 b = 0; b < B; b += 2) {
+        if (b + 1 < B) load(xb, b + 1);
+        count(xa, b);
+        if (b + 2 < B) load(xa, b + 2);
+        if (b + 1 < B) count(xb, b + 1);
+    }
+}
+
 __global__ void __launch_bounds__(32 * PLAN_WARPS)
 huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, const u8* __restrict__ src,
                 unsigned msvReq, unsigned tlogReq, Plan* __restrict__ plans, int serialHeader)
@@ -122,10 +157,13 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     u32 const seg = (n + 3) / 4;
     for (u32 i = lane; i < 4 * 256; i += 32) (&w.count4[0][0])[i] = 0;
     __syncwarp();
-    #pragma unroll 1
-    for (u32 k = 0; k < 4; k++) {
-        u32 const beg = min(k * seg, n), end = (k < 3) ? min((k + 1) * seg, n) : n;
-        warp_hist_range(w.count4[k], s, beg, end, lane);
+    if ((reinterpret_cast<u64>(s) & 15) == 0 && seg % 2048 == 0 && n == 4 * seg) warp_hist4_pipelined(w.count4, s, n, seg, lane);
+    else {
+        #pragma unroll 1
+        for (u32 k = 0; k < 4; k++) {
+            u32 const beg = min(k * seg, n), end = (k < 3) ? min((k + 1) * seg, n) : n;
+            warp_hist_range(w.count4[k], s, beg, end, lane);
+        }
     }
     __syncwarp();
     u32 top = 0, best = 0;
