@@ -420,6 +420,43 @@ FSEB_API size_t HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSi
     return (size_t)r;
 }
 
+// ---- constant-pattern tables for stored / single-symbol blocks (lib/fse.h:330-345 ; fse_compress.c:498-551, fse_decompress.c:134-176).
+//      Pure fills of the ABI table layouts: host arithmetic like the other scalar helpers, no data path involved. ----
+FSEB_API size_t FSE_buildCTable_raw(unsigned* ct, unsigned nbBits)
+{
+    if (nbBits < 1) return (size_t)err(E_GENERIC);
+    if (nbBits > 15) return (size_t)err(E_TLOG_TOO_LARGE);               // the reference would overflow its U16 cells
+    unsigned const tableSize = 1u << nbBits;
+    unsigned short* const t16 = reinterpret_cast<unsigned short*>(ct) + 2;
+    unsigned* const tt = ct + 1 + (tableSize >> 1);
+    t16[-2] = (unsigned short)nbBits; t16[-1] = (unsigned short)(tableSize - 1);
+    for (unsigned s = 0; s < tableSize; s++) t16[s] = (unsigned short)(tableSize + s);
+    for (unsigned s = 0; s < tableSize; s++) { tt[2 * s] = s - 1; tt[2 * s + 1] = (nbBits << 16) - tableSize; }
+    return 0;
+}
+FSEB_API size_t FSE_buildCTable_rle(unsigned* ct, unsigned char symbolValue)
+{
+    unsigned short* const t16 = reinterpret_cast<unsigned short*>(ct) + 2;
+    unsigned* const tt = ct + 2;
+    t16[-2] = 0; t16[-1] = symbolValue; t16[0] = 0; t16[1] = 0;
+    tt[2 * symbolValue] = 0; tt[2 * symbolValue + 1] = 0;
+    return 0;
+}
+FSEB_API size_t FSE_buildDTable_rle(unsigned* dt, unsigned char symbolValue)
+{
+    dt[0] = 0;                                                            // tableLog 0, fastMode 0
+    dt[1] = (unsigned)symbolValue << 16;                                  // { newState 0, symbol, nbBits 0 }
+    return 0;
+}
+FSEB_API size_t FSE_buildDTable_raw(unsigned* dt, unsigned nbBits)
+{
+    if (nbBits < 1) return (size_t)err(E_GENERIC);
+    if (nbBits > 15) return (size_t)err(E_TLOG_TOO_LARGE);
+    dt[0] = nbBits | (1u << 16);                                          // fastMode 1
+    for (unsigned s = 0; s < (1u << nbBits); s++) dt[1 + s] = ((s & 0xFF) << 16) | (nbBits << 24);
+    return 0;
+}
+
 // ---- payload coding with a caller-supplied table (the tables are ABI: fse.h:295-296,483-486,565-575 ; huf.h:136-149) ----
 namespace {
 constexpr size_t MICRO_MAX = (size_t)1 << 24;                           // single-call payloads above 16 MiB are refused (use the batch tier)
@@ -428,11 +465,11 @@ size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 FSEB_API size_t FSE_compress_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* ct)   // lib/fse.h:222
 {
     unsigned const tl = ct[0] & 0xFFFF, msv = ct[0] >> 16;
-    if (tl > FSE_MAX_TLOG || tl < 1) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (tl > FSE_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
     if (msv > FSE_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
     if (srcSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
     size_t const cap = dstSize < 2 * srcSize + 64 ? dstSize : 2 * srcSize + 64;     // <= 12 bits per symbol: more room can never be used
-    size_t const ctBytes = (1 + ((size_t)1 << (tl - 1)) + 2 * ((size_t)msv + 1)) * sizeof(unsigned);
+    size_t const ctBytes = (1 + (tl ? ((size_t)1 << (tl - 1)) : 1) + 2 * ((size_t)msv + 1)) * sizeof(unsigned);   // FSE_CTABLE_SIZE_U32 ; rle tables: fse_compress.c:532
     size_t const inOff = 16384, outOff = inOff + al16(srcSize + 16);
     Micro m(outOff + cap + 64);
     m.up(0, ct, ctBytes); m.up(inOff, src, srcSize);

@@ -135,6 +135,11 @@ size_t      HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_
  * reference's own ABI layouts (FSE_CTable fse.h:295,483-486 ; FSE_DTable fse.h:296,565-575 ; HUF_CElt huf_compress.c:106-109 ;
  * HUF_DTable single-symbol huf_decompress.c:101,116), e.g. as produced by FSE_buildCTable / FSE_buildDTable /
  * HUF_buildCTable / HUF_readDTableX1 above or by the CPU library.  Single synchronous calls on host buffers, <= 16 MiB. */
+/* constant-pattern tables for stored / single-symbol blocks (lib/fse.h:330-345) */
+size_t      FSE_buildCTable_raw(unsigned* ct, unsigned nbBits);
+size_t      FSE_buildCTable_rle(unsigned* ct, unsigned char symbolValue);
+size_t      FSE_buildDTable_raw(unsigned* dt, unsigned nbBits);
+size_t      FSE_buildDTable_rle(unsigned* dt, unsigned char symbolValue);
 size_t      FSE_compress_usingCTable(void* dst, size_t dstCapacity, const void* src, size_t srcSize, const unsigned* ct);
 size_t      FSE_decompress_usingDTable(void* dst, size_t dstCapacity, const void* cSrc, size_t cSrcSize, const unsigned* dt);
 size_t      HUF_compress4X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable);

@@ -57,3 +57,33 @@ def test_product_does_not_touch_the_oracle():
                     if re.search(r"fse_oracle|libfse_ref|oracle/_ref|orc_", t) and f != "_build.py":
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_constant_pattern_tables_match_the_reference():
+    """FSE_buildCTable_raw/_rle and FSE_buildDTable_raw/_rle are host-side fills of the ABI layouts: word-equal with the
+    compiled reference (fse_compress.c:498-551, fse_decompress.c:134-176)"""
+    import numpy as np
+    from helpers import load_ref, ptr
+    from finitestateentropy_b200 import _build
+    ref = load_ref()
+    if ref is None:
+        import pytest
+        pytest.skip("compiled reference not available")
+    lib = ctypes.CDLL(_build.build_lib())
+    for L in (lib, ref):
+        for n in ("FSE_buildCTable_raw", "FSE_buildDTable_raw"):
+            f = getattr(L, n); f.restype = ctypes.c_size_t; f.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        for n in ("FSE_buildCTable_rle", "FSE_buildDTable_rle"):
+            f = getattr(L, n); f.restype = ctypes.c_size_t; f.argtypes = [ctypes.c_void_p, ctypes.c_ubyte]
+    for nb in range(0, 9):
+        a = np.zeros(1 + 128 + 2 * 256 + 8, np.uint32); b = np.zeros_like(a)
+        ra, rb = lib.FSE_buildCTable_raw(ptr(a), nb), ref.FSE_buildCTable_raw(ptr(b), nb)
+        assert ra == rb and np.array_equal(a, b)
+        a = np.zeros(1 + 256 + 8, np.uint32); b = np.zeros_like(a)
+        ra, rb = lib.FSE_buildDTable_raw(ptr(a), nb), ref.FSE_buildDTable_raw(ptr(b), nb)
+        assert ra == rb and np.array_equal(a, b)
+    for sym in (0, 1, 77, 255):
+        a = np.zeros(2 + 2 * 256 + 8, np.uint32); b = np.zeros_like(a)
+        assert lib.FSE_buildCTable_rle(ptr(a), sym) == ref.FSE_buildCTable_rle(ptr(b), sym) == 0 and np.array_equal(a, b)
+        a = np.zeros(4, np.uint32); b = np.zeros_like(a)
+        assert lib.FSE_buildDTable_rle(ptr(a), sym) == ref.FSE_buildDTable_rle(ptr(b), sym) == 0 and np.array_equal(a, b)

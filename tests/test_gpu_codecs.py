@@ -303,3 +303,41 @@ def test_large_roundtrip_property(codec, p, mib):
     got = cbuf[:64 * SLOT].cpu().numpy()
     for b in range(64):
         assert np.array_equal(got[b * SLOT: b * SLOT + int(wcs[b])], wc[b * SLOT: b * SLOT + int(wcs[b])])
+
+
+def test_raw_and_rle_tables_through_payload_calls():
+    """FSE_buildCTable_raw/_rle + FSE_buildDTable_raw/_rle images driven through FSE_compress_usingCTable /
+    FSE_decompress_usingDTable on the GPU vs the compiled reference (fullbench.c:595-629 call pattern)"""
+    lib, isref = checker()
+    if not isref:
+        pytest.skip("needs the compiled reference")
+    L = fb.lib()
+    def sig(M, n, *a):
+        f = getattr(M, n); f.restype = C.c_size_t; f.argtypes = list(a); return f
+    for M in (L, lib):
+        sig(M, "FSE_buildCTable_raw", C.c_void_p, U); sig(M, "FSE_buildDTable_raw", C.c_void_p, U)
+        sig(M, "FSE_buildCTable_rle", C.c_void_p, C.c_ubyte); sig(M, "FSE_buildDTable_rle", C.c_void_p, C.c_ubyte)
+        sig(M, "FSE_compress_usingCTable", C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+        sig(M, "FSE_decompress_usingDTable", C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+    rng = np.random.default_rng(77)
+    for nb in (1, 3, 6, 8):
+        n = int(rng.integers(50, 5000))
+        d = rng.integers(0, 1 << nb, n, dtype=np.uint8)
+        ct = np.zeros(1 + 128 + 2 * 256 + 8, np.uint32); dt = np.zeros(1 + 256 + 8, np.uint32)
+        assert L.FSE_buildCTable_raw(ptr(ct), nb) == 0 and L.FSE_buildDTable_raw(ptr(dt), nb) == 0
+        cap = n + 64
+        oa = np.zeros(cap + 16, np.uint8); ob = np.zeros(cap + 16, np.uint8)
+        ea = L.FSE_compress_usingCTable(ptr(oa), cap, ptr(d), n, ptr(ct)); eb = lib.FSE_compress_usingCTable(ptr(ob), cap, ptr(d), n, ptr(ct))
+        assert ea == eb and bytes(oa[:ea]) == bytes(ob[:eb])
+        if ea:
+            ra = np.zeros(n + 8, np.uint8); rb = np.zeros(n + 8, np.uint8)
+            da = L.FSE_decompress_usingDTable(ptr(ra), n, ptr(oa), ea, ptr(dt)); db = lib.FSE_decompress_usingDTable(ptr(rb), n, ptr(ob), eb, ptr(dt))
+            assert da == db == n and bytes(ra[:n]) == bytes(rb[:n]) == bytes(d)
+    for sym in (0, 200):
+        n = 777
+        d = np.full(n, sym, np.uint8)
+        ct = np.zeros(2 + 2 * 256 + 8, np.uint32); dt = np.zeros(4, np.uint32)
+        assert L.FSE_buildCTable_rle(ptr(ct), sym) == 0 and L.FSE_buildDTable_rle(ptr(dt), sym) == 0
+        oa = np.zeros(128, np.uint8); ob = np.zeros(128, np.uint8)
+        ea = L.FSE_compress_usingCTable(ptr(oa), 100, ptr(d), n, ptr(ct)); eb = lib.FSE_compress_usingCTable(ptr(ob), 100, ptr(d), n, ptr(ct))
+        assert ea == eb and bytes(oa[:ea]) == bytes(ob[:eb])
