@@ -520,6 +520,73 @@ FSEB_API size_t HUF_decompress4X_usingDTable(void* dst, size_t maxDstSize, const
     return HUF_decompress4X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);
 }
 
+// ---- single-stream Huff0 (lib/huf.h:288-320): the same device routines with one stream; HUF_compress1X is the reference's
+//      driver (huf_compress.c:637-724 with HUF_singleStream) composed from the table-level calls above ----
+FSEB_API size_t HUF_compress1X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable)      // lib/huf.h:290
+{
+    if (srcSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const cap = dstSize < 2 * srcSize + 64 ? dstSize : 2 * srcSize + 64;
+    size_t const inOff = 4096, outOff = inOff + al16(srcSize + 16);
+    Micro m(outOff + cap + 64);
+    m.up(0, CTable, 256 * sizeof(unsigned)); m.up(inOff, src, srcSize);
+    u64 const r = m.run(MOP_HUF_ENCODE1X_CT, srcSize, cap, inOff, outOff);
+    if (!is_err(r) && r) m.down(dst, outOff, (size_t)r);
+    return (size_t)r;
+}
+FSEB_API size_t HUF_compress1X(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned huffLog)   // lib/huf.h:288
+{
+    unsigned char* const ostart = (unsigned char*)dst;
+    if (!srcSize || !dstSize) return 0;                                              // huf_compress.c:656-657
+    if (srcSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
+    if (huffLog > HUF_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (maxSymbolValue > HUF_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    if (!maxSymbolValue) maxSymbolValue = HUF_MAX_SV;
+    if (!huffLog) huffLog = HUF_DEF_TLOG;
+    unsigned count[256]; unsigned ctable[256];
+    size_t const largest = HIST_count(count, &maxSymbolValue, src, srcSize);
+    if (is_err(largest)) return largest;
+    if (largest == srcSize) { ostart[0] = ((const unsigned char*)src)[0]; return 1; }   // :673
+    if (largest <= (srcSize >> 7) + 4) return 0;                                     // :674
+    huffLog = HUF_optimalTableLog(huffLog, srcSize, maxSymbolValue);
+    size_t const maxBits = HUF_buildCTable(ctable, count, maxSymbolValue, huffLog);
+    if (is_err(maxBits)) return maxBits;
+    huffLog = (unsigned)maxBits;
+    for (unsigned s = maxSymbolValue + 1; s < 256; s++) ctable[s] = 0;
+    size_t const hSize = HUF_writeCTable(ostart, dstSize, ctable, maxSymbolValue, huffLog);
+    if (is_err(hSize)) return hSize;
+    if (hSize + 12ul >= srcSize) return 0;                                           // :715
+    size_t const cSize = HUF_compress1X_usingCTable(ostart + hSize, dstSize - hSize, src, srcSize, ctable);
+    if (is_err(cSize)) return cSize;
+    if (cSize == 0) return 0;
+    if (hSize + cSize >= srcSize - 1) return 0;                                      // :625
+    return hSize + cSize;
+}
+FSEB_API size_t HUF_decompress1X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)  // lib/huf.h:320
+{
+    unsigned const type = (DTable[0] >> 8) & 0xFF, tl = (DTable[0] >> 16) & 0xFF;
+    if (type != 0) return (size_t)err(E_GENERIC);                                   // huf_decompress.c:367
+    if (tl > HUF_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (cSrcSize > MICRO_MAX || maxDstSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const inOff = 16384, outOff = inOff + al16(cSrcSize + 16);
+    Micro m(outOff + maxDstSize + 64);
+    m.up(0, DTable, sizeof(unsigned) + ((size_t)1 << tl) * 2); m.up(inOff, cSrc, cSrcSize);
+    u64 const r = m.run(MOP_HUF_DECODE1X1_DT, cSrcSize, maxDstSize, inOff, outOff);
+    if (!is_err(r)) m.down(dst, outOff, maxDstSize);
+    return (size_t)r;
+}
+FSEB_API size_t HUF_decompress1X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)   // lib/huf.h:318
+{
+    return HUF_decompress1X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);   // only single-symbol tables exist here (see HUF_decompress4X_usingDTable)
+}
+FSEB_API size_t HUF_decompress1X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                                          // lib/huf.h:302
+{
+    unsigned DTable[1 + 2048]; DTable[0] = 11u * 0x01000001u;                       // HUF_CREATE_STATIC_DTABLEX1(DTable, HUF_TABLELOG_MAX)
+    size_t const hSize = HUF_readDTableX1(DTable, cSrc, cSrcSize);
+    if (is_err(hSize)) return hSize;
+    if (hSize >= cSrcSize) return (size_t)err(E_SRC_WRONG);                         // huf_decompress.c:380
+    return HUF_decompress1X1_usingDTable(dst, dstSize, (const unsigned char*)cSrc + hSize, cSrcSize - hSize, DTable);
+}
+
 // ================================================================================================
 // measurement inputs (programs/probaGenerator.c:95-126, programs/fuzzerU16.c:107-134) generated in HBM
 // ================================================================================================

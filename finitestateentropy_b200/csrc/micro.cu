@@ -201,6 +201,33 @@ __global__ void __launch_bounds__(256) micro_kernel(int op, MicroArgs A, u8* buf
             *ret = r;
         }
         break; }
+    case MOP_HUF_ENCODE1X_CT: {    // HUF_compress1X_usingCTable (huf_compress.c:457-502): one stream, last symbol first
+        if (tid == 0) {
+            const u32* const ct = (const u32*)buf; const u8* const in = buf + A.a[2];
+            u64 const n = A.a[0], cap = A.a[1];
+            if (cap < 8) { *ret = 0; break; }                                        // :470
+            BitSink sk; sink_open(sk, buf + A.a[3], cap);
+            if (!sk.usable) { *ret = 0; break; }
+            for (u64 i = n; i-- > 0;) { u32 const e = ct[in[i]]; sink_put(sk, e & 0xFFFF, e >> 16); }
+            *ret = sink_close(sk);
+        }
+        break; }
+    case MOP_HUF_DECODE1X1_DT: {   // HUF_decompress1X1_usingDTable (huf_decompress.c:240-260)
+        if (tid == 0) {
+            const u32* const dtab = (const u32*)buf;
+            const u16* const cells = (const u16*)(dtab + 1);
+            u32 const dtLog = (dtab[0] >> 16) & 0xFF;
+            u8* const out = buf + A.a[3];
+            long long p = 0; long long const pe = (long long)A.a[1];
+            BitSrc b;
+            u64 const e = bs_open(b, buf + A.a[2], A.a[0]);
+            if (is_err(e)) { *ret = e; break; }
+            auto sym = [&]() { u32 const cell = cells[bs_peek_fast(b, dtLog)]; b.used += cell >> 8; out[p++] = (u8)cell; };
+            while ((bs_refill(b) == SRC_MORE) & (p < pe - 3)) { sym(); sym(); sym(); sym(); }
+            while (p < pe) sym();
+            *ret = bs_exhausted(b) ? (u64)pe : err(E_CORRUPT);
+        }
+        break; }
     default: if (tid == 0) *ret = err(E_GENERIC);
     }
 }

@@ -145,6 +145,12 @@ size_t      FSE_decompress_usingDTable(void* dst, size_t dstCapacity, const void
 size_t      HUF_compress4X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable);
 size_t      HUF_decompress4X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
 size_t      HUF_decompress4X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
+/* single-stream Huff0 (lib/huf.h:288-320) */
+size_t      HUF_compress1X(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned tableLog);
+size_t      HUF_compress1X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable);
+size_t      HUF_decompress1X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
+size_t      HUF_decompress1X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
+size_t      HUF_decompress1X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
 /* lib/fseU16.h:75-79 */
 size_t      FSE_compressU16(void* dst, size_t dstCapacity, const unsigned short* src, size_t srcSize,
                             unsigned maxSymbolValue, unsigned tableLog);

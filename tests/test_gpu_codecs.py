@@ -341,3 +341,45 @@ def test_raw_and_rle_tables_through_payload_calls():
         oa = np.zeros(128, np.uint8); ob = np.zeros(128, np.uint8)
         ea = L.FSE_compress_usingCTable(ptr(oa), 100, ptr(d), n, ptr(ct)); eb = lib.FSE_compress_usingCTable(ptr(ob), 100, ptr(d), n, ptr(ct))
         assert ea == eb and bytes(oa[:ea]) == bytes(ob[:eb])
+
+
+def test_single_stream_huff0():
+    """HUF_compress1X / HUF_compress1X_usingCTable / HUF_decompress1X1 / HUF_decompress1X_usingDTable vs the compiled reference"""
+    lib, isref = checker()
+    if not isref:
+        pytest.skip("needs the compiled reference")
+    L = fb.lib()
+    for M in (L, lib):
+        for n_, a_ in (("HUF_compress1X", [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, U, U]),
+                       ("HUF_decompress1X1", [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+                       ("HUF_compress1X_usingCTable", [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+                       ("HUF_buildCTable", [C.c_void_p, C.c_void_p, U, U]),
+                       ("HIST_count", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t])):
+            f = getattr(M, n_); f.restype = C.c_size_t; f.argtypes = a_
+    rng = np.random.default_rng(91)
+    for it in range(14):
+        n = int(rng.integers(1, 30000)) if it else 20000
+        d = zoo(rng, n)
+        for cap in (n + 300, max(1, n // 2)):
+            oa = np.zeros(cap + 16, np.uint8); ob = np.zeros(cap + 16, np.uint8)
+            ea = L.HUF_compress1X(ptr(oa), cap, ptr(d), n, 255, 11); eb = lib.HUF_compress1X(ptr(ob), cap, ptr(d), n, 255, 11)
+            assert ea == eb, (it, n, cap, ea, eb)
+            if is_error(ea) or ea <= 1:
+                continue
+            assert bytes(oa[:ea]) == bytes(ob[:eb])
+            ra = np.zeros(n + 8, np.uint8); rb = np.zeros(n + 8, np.uint8)
+            da = L.HUF_decompress1X1(ptr(ra), n, ptr(oa), ea); db = lib.HUF_decompress1X1(ptr(rb), n, ptr(ob), eb)
+            assert da == db == n and bytes(ra[:n]) == bytes(d[:n])
+            bad = oa[:ea].copy(); bad[int(rng.integers(0, ea))] ^= 1 << int(rng.integers(0, 8))
+            da = L.HUF_decompress1X1(ptr(ra), n, ptr(bad), ea); db = lib.HUF_decompress1X1(ptr(rb), n, ptr(bad), ea)
+            assert da == db
+        # payload only, with the reference's own table
+        cnt = (U * 256)(); m = U(255)
+        if is_error(lib.HIST_count(cnt, C.byref(m), ptr(d), n)) or m.value == 0:
+            continue
+        ct = np.zeros(256, np.uint32)
+        if is_error(lib.HUF_buildCTable(ptr(ct), cnt, m.value, 11)):
+            continue
+        oa = np.zeros(n + 300, np.uint8); ob = np.zeros(n + 300, np.uint8)
+        ea = L.HUF_compress1X_usingCTable(ptr(oa), n + 256, ptr(d), n, ptr(ct)); eb = lib.HUF_compress1X_usingCTable(ptr(ob), n + 256, ptr(d), n, ptr(ct))
+        assert ea == eb and bytes(oa[:ea]) == bytes(ob[:eb])
