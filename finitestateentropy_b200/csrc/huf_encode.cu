@@ -303,17 +303,22 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             else { u8* const pb = reinterpret_cast<u8*>(gw + j); for (u32 t = 0; t < 4; t++) if (lo + t >= a0 && lo + t < endByte) pb[t] = (u8)(v >> (8 * t)); }
         };
         auto flush = [&](bool all) {
-            __syncwarp();
             u32 const upTo = all ? (endByte + 3) / 4 : (bitpos >> 5);
+            if (!all && flushed + 32 > upTo) return;                // warp-uniform: fewer than 32 final words pending
+            __syncwarp();
             while (all ? flushed < upTo : flushed + 32 <= upTo) {
                 u32 const j = flushed + lane;
-                if (j < upTo) { u32 const v = win[j & (W - 1)]; win[j & (W - 1)] = 0; store_word(j, v); }
+                if (j < upTo) {
+                    u32 const v = win[j & (W - 1)]; win[j & (W - 1)] = 0;
+                    if (!all && (j != 0 || a0 == 0)) gw[j] = v;     // interior word: every bit below bitpos is final and inside the stream
+                    else store_word(j, v);                          // first / last word: byte-exact
+                }
                 flushed += 32;
             }
         };
-        auto place = [&](u32 a0, u32 a1, u32 held) -> u32 {         // lane's `held` bits go to bitpos + exclusive prefix
+        auto place = [&](u32 x0, u32 x1, u32 held) -> u32 {         // lane's `held` bits go to bitpos + exclusive prefix
             u32 excl; u32 const sum = scan(held, excl);
-            put(bitpos + excl, a0, a1);
+            put(bitpos + excl, x0, x1);
             return sum;
         };
         constexpr int PF = 4;
@@ -449,12 +454,13 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
     size_t const need = sizeof(hufe::Plan) * (size_t)g.nBlocks;
     if (asyncScratch) e = cudaMallocAsync((void**)&plans, need, stream);
     else {
-        struct Slot { cudaStream_t s; void* p; size_t cap; };
+        struct Slot { int dev; cudaStream_t s; void* p; size_t cap; };
         static std::mutex mu; static std::vector<Slot> slots;
         std::lock_guard<std::mutex> lock(mu);
+        int dev = 0; cudaGetDevice(&dev);                           // the legacy stream handle is the same on every device
         Slot* hit = nullptr;
-        for (auto& sl : slots) if (sl.s == stream) { hit = &sl; break; }
-        if (!hit) { slots.push_back(Slot{ stream, nullptr, 0 }); hit = &slots.back(); }
+        for (auto& sl : slots) if (sl.s == stream && sl.dev == dev) { hit = &sl; break; }
+        if (!hit) { slots.push_back(Slot{ dev, stream, nullptr, 0 }); hit = &slots.back(); }
         e = cudaSuccess;
         if (hit->cap < need) {
             if (hit->p) { cudaStreamSynchronize(stream); cudaFree(hit->p); hit->p = nullptr; hit->cap = 0; }
