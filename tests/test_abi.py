@@ -87,3 +87,28 @@ def test_constant_pattern_tables_match_the_reference():
         assert lib.FSE_buildCTable_rle(ptr(a), sym) == ref.FSE_buildCTable_rle(ptr(b), sym) == 0 and np.array_equal(a, b)
         a = np.zeros(4, np.uint32); b = np.zeros_like(a)
         assert lib.FSE_buildDTable_rle(ptr(a), sym) == ref.FSE_buildDTable_rle(ptr(b), sym) == 0 and np.array_equal(a, b)
+
+
+def test_prototypes_have_the_reference_arity():
+    """Every reference-named entry point declared in include/fse_b200.h takes as many parameters as the declaration of the
+    same name in the reference's own headers (lib/fse.h, huf.h, hist.h, fseU16.h).  Runs only where the tree is mounted."""
+    import pytest
+    ref = "/root/reference/lib"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+
+    def protos(text):
+        text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S); text = re.sub(r"//[^\n]*", " ", text)
+        out = {}
+        for m in re.finditer(r"\b((?:FSE|HUF|HIST)_\w+)\s*\(([^;{}()]*)\)\s*;", text):
+            args = m.group(2).strip()
+            out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+    theirs = {}
+    for h in ("fse.h", "huf.h", "hist.h", "fseU16.h"):
+        theirs.update(protos(open(os.path.join(ref, h)).read()))
+    ours = protos(open(os.path.join(ROOT, "include", "fse_b200.h")).read())
+    common = sorted(set(ours) & set(theirs))
+    assert len(common) >= 40, common
+    bad = [(n, ours[n], theirs[n]) for n in common if ours[n] != theirs[n]]
+    assert not bad, bad
