@@ -420,6 +420,22 @@ FSEB_API size_t HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSi
     return (size_t)r;
 }
 
+// ---- CTable inspection helpers (lib/huf.h:196-199,221): arithmetic on the 4-byte cells {U16 val; BYTE nbBits} ----
+FSEB_API unsigned HUF_getNbBits(const void* symbolTable, unsigned symbolValue)                                      // huf_compress.c:200-205
+{ return (((const unsigned*)symbolTable)[symbolValue] >> 16) & 0xFF; }
+FSEB_API size_t HUF_estimateCompressedSize(const unsigned* CTable, const unsigned* count, unsigned maxSymbolValue)  // huf_compress.c:422-430
+{
+    size_t nbBits = 0;
+    for (unsigned s = 0; s <= maxSymbolValue; s++) nbBits += (size_t)((CTable[s] >> 16) & 0xFF) * count[s];
+    return nbBits >> 3;
+}
+FSEB_API int HUF_validateCTable(const unsigned* CTable, const unsigned* count, unsigned maxSymbolValue)             // huf_compress.c:432-439
+{
+    int bad = 0;
+    for (unsigned s = 0; s <= maxSymbolValue; s++) bad |= (count[s] != 0) & (((CTable[s] >> 16) & 0xFF) == 0);
+    return !bad;
+}
+
 // ---- constant-pattern tables for stored / single-symbol blocks (lib/fse.h:330-345 ; fse_compress.c:498-551, fse_decompress.c:134-176).
 //      Pure fills of the ABI table layouts: host arithmetic like the other scalar helpers, no data path involved. ----
 FSEB_API size_t FSE_buildCTable_raw(unsigned* ct, unsigned nbBits)

@@ -135,6 +135,10 @@ size_t      HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_
  * reference's own ABI layouts (FSE_CTable fse.h:295,483-486 ; FSE_DTable fse.h:296,565-575 ; HUF_CElt huf_compress.c:106-109 ;
  * HUF_DTable single-symbol huf_decompress.c:101,116), e.g. as produced by FSE_buildCTable / FSE_buildDTable /
  * HUF_buildCTable / HUF_readDTableX1 above or by the CPU library.  Single synchronous calls on host buffers, <= 16 MiB. */
+/* CTable inspection helpers (lib/huf.h:196-199,221) */
+unsigned    HUF_getNbBits(const void* symbolTable, unsigned symbolValue);
+size_t      HUF_estimateCompressedSize(const unsigned* CTable, const unsigned* count, unsigned maxSymbolValue);
+int         HUF_validateCTable(const unsigned* CTable, const unsigned* count, unsigned maxSymbolValue);
 /* constant-pattern tables for stored / single-symbol blocks (lib/fse.h:330-345) */
 size_t      FSE_buildCTable_raw(unsigned* ct, unsigned nbBits);
 size_t      FSE_buildCTable_rle(unsigned* ct, unsigned char symbolValue);

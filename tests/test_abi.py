@@ -112,3 +112,36 @@ def test_prototypes_have_the_reference_arity():
     assert len(common) >= 40, common
     bad = [(n, ours[n], theirs[n]) for n in common if ours[n] != theirs[n]]
     assert not bad, bad
+
+
+def test_ctable_helpers_match_the_reference():
+    """HUF_getNbBits / HUF_estimateCompressedSize / HUF_validateCTable: host arithmetic on CTable cells, equal to the reference"""
+    import numpy as np
+    from helpers import load_ref, ptr
+    from finitestateentropy_b200 import _build
+    ref = load_ref()
+    if ref is None:
+        import pytest
+        pytest.skip("compiled reference not available")
+    lib = ctypes.CDLL(_build.build_lib())
+    U = ctypes.c_uint
+    for L in (lib, ref):
+        L.HUF_getNbBits.restype = U; L.HUF_getNbBits.argtypes = [ctypes.c_void_p, U]
+        L.HUF_estimateCompressedSize.restype = ctypes.c_size_t; L.HUF_estimateCompressedSize.argtypes = [ctypes.c_void_p, ctypes.c_void_p, U]
+        L.HUF_validateCTable.restype = ctypes.c_int; L.HUF_validateCTable.argtypes = [ctypes.c_void_p, ctypes.c_void_p, U]
+    ref.HUF_buildCTable.restype = ctypes.c_size_t; ref.HUF_buildCTable.argtypes = [ctypes.c_void_p, ctypes.c_void_p, U, U]
+    rng = np.random.default_rng(5)
+    for it in range(20):
+        msv = int(rng.integers(1, 256))
+        cnt = rng.integers(0, 500, 256).astype(np.uint32); cnt[msv] = max(1, int(cnt[msv])); cnt[0] = max(1, int(cnt[0]))
+        ct = np.zeros(256, np.uint32)
+        r = ref.HUF_buildCTable(ptr(ct), ptr(cnt), msv, 11)
+        assert r < 2 ** 63
+        assert lib.HUF_estimateCompressedSize(ptr(ct), ptr(cnt), msv) == ref.HUF_estimateCompressedSize(ptr(ct), ptr(cnt), msv)
+        assert lib.HUF_validateCTable(ptr(ct), ptr(cnt), msv) == ref.HUF_validateCTable(ptr(ct), ptr(cnt), msv) == 1
+        cnt2 = cnt.copy(); z = [s for s in range(msv + 1) if (ct[s] >> 16) & 0xFF == 0]
+        if z:
+            cnt2[z[0]] = 3
+            assert lib.HUF_validateCTable(ptr(ct), ptr(cnt2), msv) == ref.HUF_validateCTable(ptr(ct), ptr(cnt2), msv) == 0
+        for s in (0, msv // 2, msv):
+            assert lib.HUF_getNbBits(ptr(ct), s) == ref.HUF_getNbBits(ptr(ct), s)
