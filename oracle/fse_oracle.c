@@ -957,6 +957,72 @@ size_t orc_huf_read_dtable_x1(u32* dtable, const void* src, size_t srcSize)
     return h;
 }
 
+/* a18  HUF_readDTableX2 (lib/huf_decompress.c:551-649 ; fill :468-549): the double-symbol table, always built at the
+ * descriptor's maxTableLog L.  Cell = { U16 sequence; BYTE nbBits; BYTE length } (:460).
+ * Formulation: symbols of weight >= 1 are listed by (weight, symbol).  In an index space of width L a symbol of code
+ * length n owns 2^(L-n) consecutive cells, weights ascending, so weight w starts at first[w] = sum_{v<w} count[v] << (v+L-tl-1).
+ * If the cells of a first symbol (L-n index bits left) can hold the shortest code, they are a scaled copy of the same
+ * layout for the second symbol: weight w starts at first[w] >> n; second symbols too long to fit (weight < n + tl+1-L, at
+ * least 1) leave the leading cells as single-symbol entries.  */
+size_t orc_huf_read_dtable_x2(u32* dtable, const void* src, size_t srcSize)
+{
+    u8 weights[HUF_MAX_SV + 1];
+    u32 rank[16 + 1];
+    u8 listSym[HUF_MAX_SV + 1], listW[HUF_MAX_SV + 1];
+    u32 listStart[HUF_MAX_TLOG + 2], fill[HUF_MAX_TLOG + 2], first[HUF_MAX_TLOG + 2];
+    u32 tl = 0, nbSym = 0, maxW, w, s, listSize = 0;
+    u32 const L = dtable[0] & 0xFF;
+    u32* const cells = dtable + 1;
+    size_t h;
+    if (L > HUF_MAX_TLOG) return ORC_ERROR(ORC_TLOG_TOO_LARGE);          /* :586 */
+    h = orc_huf_read_stats(weights, HUF_MAX_SV + 1, rank, &nbSym, &tl, src, srcSize);
+    if (orc_is_error(h)) return h;
+    if (tl > L) return ORC_ERROR(ORC_TLOG_TOO_LARGE);                     /* :593 */
+    for (maxW = tl; rank[maxW] == 0; maxW--) {}
+    /* symbols of weight >= 1 ordered by (weight, symbol) */
+    for (w = 1; w <= maxW; w++) { listStart[w] = listSize; listSize += rank[w]; }
+    listStart[maxW + 1] = listSize;
+    for (w = 1; w <= maxW; w++) fill[w] = listStart[w];
+    for (s = 0; s < nbSym; s++) { u32 const ws = weights[s]; if (ws) { listSym[fill[ws]] = (u8)s; listW[fill[ws]] = (u8)ws; fill[ws]++; } }
+    {   u32 acc = 0;
+        for (w = 1; w <= maxW; w++) { first[w] = acc; acc += rank[w] << (w + (L - tl) - 1); }
+    }
+    {   u32 const minBits = tl + 1 - maxW;                                /* shortest code */
+        u32 next1[HUF_MAX_TLOG + 2];
+        u32 i;
+        for (w = 1; w <= maxW; w++) next1[w] = first[w];
+        for (i = 0; i < listSize; i++) {
+            u32 const sym = listSym[i], w1 = listW[i], n = tl + 1 - w1;
+            u32 const start = next1[w1], span = 1u << (L - n);
+            u32* const sub = cells + start;
+            next1[w1] += span;
+            if (L - n >= minBits) {                                       /* room for a second symbol */
+                int minWeight = (int)n + ((int)tl + 1 - (int)L);
+                u32 next2[HUF_MAX_TLOG + 2];
+                u32 j, u;
+                if (minWeight < 1) minWeight = 1;
+                for (w = 1; w <= maxW; w++) next2[w] = first[w] >> n;
+                if (minWeight > 1) {                                      /* too-long second symbols: single-symbol cells */
+                    u32 const skip = next2[minWeight];
+                    for (u = 0; u < skip; u++) sub[u] = sym | (n << 16) | (1u << 24);
+                }
+                for (j = listStart[minWeight]; j < listSize; j++) {
+                    u32 const s2 = listSym[j], w2 = listW[j], n2 = tl + 1 - w2;
+                    u32 const len2 = 1u << (L - n - n2);
+                    u32 const at = next2[w2];
+                    for (u = 0; u < len2; u++) sub[at + u] = ((sym + (s2 << 8)) & 0xFFFF) | ((n + n2) << 16) | (2u << 24);
+                    next2[w2] += len2;
+                }
+            } else {
+                u32 u;
+                for (u = 0; u < span; u++) sub[u] = sym | (n << 16) | (1u << 24);
+            }
+        }
+    }
+    dtable[0] = (dtable[0] & 0xFF0000FFu) | (1u << 8) | (L << 16);         /* tableType 1, tableLog = maxTableLog (:645-647) */
+    return h;
+}
+
 /* a19  HUF_decompress1X1/4X1_usingDTable_internal_body (lib/huf_decompress.c:194-354) */
 static u8 huf_step(bsrc* b, const u16* cells, unsigned dtLog)          /* :194-201 */
 {

@@ -63,6 +63,7 @@ size_t orc_huf_read_stats(uint8_t* weights, size_t hwSize, uint32_t* rankStats, 
                           uint32_t* tableLogPtr, const void* src, size_t srcSize);
 /* DTable X1 = {maxTableLog,tableType,tableLog,reserved} + {byte,nbBits}[2^tableLog] (lib/huf_decompress.c:99-116) */
 size_t orc_huf_read_dtable_x1(uint32_t* dtable, const void* src, size_t srcSize);
+size_t orc_huf_read_dtable_x2(uint32_t* dtable, const void* src, size_t srcSize);   /* a18: double-symbol table image */
 size_t orc_huf_decode4x1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const uint32_t* dtable);
 size_t orc_huf_decode1x1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const uint32_t* dtable);
 size_t orc_huf_decompress(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);

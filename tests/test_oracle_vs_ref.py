@@ -275,6 +275,14 @@ def test_huf_tables():
         assert port.orc_huf_read_dtable_x1(ptr(dA), ptr(ha), wa) == ref.HUF_readDTableX1(ptr(dB), ptr(hb), wb) == wa
         ncell = 1 + ((1 << tA.value) + 1) // 2
         assert np.array_equal(dA[:ncell], dB[:ncell])
+        # double-symbol table image (a18), built at the descriptor's maxTableLog
+        for L in (12, 11):
+            xA = np.zeros(1 + 4096, np.uint32); xB = np.zeros(1 + 4096, np.uint32)
+            xA[0] = xB[0] = L * 0x01000001
+            qa = port.orc_huf_read_dtable_x2(ptr(xA), ptr(ha), wa); qb = ref.HUF_readDTableX2(ptr(xB), ptr(hb), wb)
+            assert qa == qb, (it, L, qa, qb)
+            if not is_error(qa):
+                assert np.array_equal(xA[:1 + (1 << L)], xB[:1 + (1 << L)]), (it, L)
         # stream codecs on the shared tables
         ca = np.zeros(BOUND(n), np.uint8); cb = np.zeros(BOUND(n), np.uint8)
         for enc_a, enc_b, dec_a, dec_b in ((port.orc_huf_encode4x, ref.HUF_compress4X_usingCTable, port.orc_huf_decode4x1, ref.HUF_decompress4X1_usingDTable),
