@@ -529,11 +529,30 @@ FSEB_API size_t HUF_decompress4X1_usingDTable(void* dst, size_t maxDstSize, cons
     if (!is_err(r)) m.down(dst, outOff, maxDstSize);
     return (size_t)r;
 }
+namespace {
+size_t huf_decode_x2(int opcode, void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)
+{
+    unsigned const type = (DTable[0] >> 8) & 0xFF, tl = (DTable[0] >> 16) & 0xFF;
+    if (type != 1) return (size_t)err(E_GENERIC);                                   // huf_decompress.c:866,910
+    if (tl > HUF_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (cSrcSize > MICRO_MAX || maxDstSize > MICRO_MAX) return (size_t)err(E_SRC_WRONG);
+    size_t const inOff = 32768, outOff = inOff + al16(cSrcSize + 16);
+    Micro m(outOff + maxDstSize + 64);
+    m.up(0, DTable, sizeof(unsigned) * (1 + ((size_t)1 << tl))); m.up(inOff, cSrc, cSrcSize);
+    u64 const r = m.run(opcode, cSrcSize, maxDstSize, inOff, outOff);
+    if (!is_err(r)) m.down(dst, outOff, maxDstSize);
+    return (size_t)r;
+}
+}
+FSEB_API size_t HUF_decompress4X2_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)   // lib/huf.h:280
+{ return huf_decode_x2(MOP_HUF_DECODE4X2_DT, dst, maxDstSize, cSrc, cSrcSize, DTable); }
+FSEB_API size_t HUF_decompress1X2_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)   // lib/huf.h:323
+{ return huf_decode_x2(MOP_HUF_DECODE1X2_DT, dst, maxDstSize, cSrc, cSrcSize, DTable); }
 FSEB_API size_t HUF_decompress4X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)    // lib/huf.h:203
 {
-    // huf_decompress.c:980-997 dispatches on DTableDesc.tableType; double-symbol (X2) images are not produced by this library
-    // (HUF_readDTableX2 is not exported), so only single-symbol tables can reach here
-    return HUF_decompress4X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);
+    // huf_decompress.c:980-997: dispatch on DTableDesc.tableType
+    return ((DTable[0] >> 8) & 0xFF) ? HUF_decompress4X2_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable)
+                                     : HUF_decompress4X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);
 }
 
 // ---- single-stream Huff0 (lib/huf.h:288-320): the same device routines with one stream; HUF_compress1X is the reference's
@@ -592,7 +611,8 @@ FSEB_API size_t HUF_decompress1X1_usingDTable(void* dst, size_t maxDstSize, cons
 }
 FSEB_API size_t HUF_decompress1X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)   // lib/huf.h:318
 {
-    return HUF_decompress1X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);   // only single-symbol tables exist here (see HUF_decompress4X_usingDTable)
+    return ((DTable[0] >> 8) & 0xFF) ? HUF_decompress1X2_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable)      // huf_decompress.c:962-977
+                                     : HUF_decompress1X1_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable);
 }
 FSEB_API size_t HUF_decompress1X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                                          // lib/huf.h:302
 {
@@ -601,6 +621,18 @@ FSEB_API size_t HUF_decompress1X1(void* dst, size_t dstSize, const void* cSrc, s
     if (is_err(hSize)) return hSize;
     if (hSize >= cSrcSize) return (size_t)err(E_SRC_WRONG);                         // huf_decompress.c:380
     return HUF_decompress1X1_usingDTable(dst, dstSize, (const unsigned char*)cSrc + hSize, cSrcSize - hSize, DTable);
+}
+
+FSEB_API size_t HUF_readDTableX2(unsigned* DTable, const void* src, size_t srcSize)                                    // lib/huf.h:268
+{
+    Micro m;
+    size_t const take = srcSize > 256 ? 256 : srcSize;
+    m.up(0, src, take);
+    u64 const r = m.run(MOP_HUF_READ_DTABLE_X2, take, DTable[0]);
+    if (is_err(r)) return (size_t)r;
+    unsigned const L = DTable[0] & 0xFF;
+    m.down(DTable, 32768, sizeof(unsigned) * (1 + ((size_t)1 << L)));
+    return (size_t)r;
 }
 
 // ================================================================================================

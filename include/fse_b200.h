@@ -128,6 +128,7 @@ size_t      HUF_writeCTable(void* dst, size_t maxDstSize, const unsigned* CTable
 size_t      HUF_readStats(unsigned char* huffWeight, size_t hwSize, unsigned* rankStats, unsigned* nbSymbolsPtr,
                           unsigned* tableLogPtr, const void* src, size_t srcSize);
 size_t      HUF_readDTableX1(unsigned* DTable, const void* src, size_t srcSize);
+size_t      HUF_readDTableX2(unsigned* DTable, const void* src, size_t srcSize);   /* double-symbol table image (huf_decompress.c:551-649) */
 unsigned    HUF_selectDecoder(size_t dstSize, size_t cSrcSize);
 size_t      HUF_decompress4X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
 size_t      HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
@@ -149,6 +150,8 @@ size_t      FSE_decompress_usingDTable(void* dst, size_t dstCapacity, const void
 size_t      HUF_compress4X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable);
 size_t      HUF_decompress4X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
 size_t      HUF_decompress4X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
+size_t      HUF_decompress4X2_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
+size_t      HUF_decompress1X2_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
 /* single-stream Huff0 (lib/huf.h:288-320) */
 size_t      HUF_compress1X(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned tableLog);
 size_t      HUF_compress1X_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* CTable);

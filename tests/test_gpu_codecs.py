@@ -383,3 +383,60 @@ def test_single_stream_huff0():
         oa = np.zeros(n + 300, np.uint8); ob = np.zeros(n + 300, np.uint8)
         ea = L.HUF_compress1X_usingCTable(ptr(oa), n + 256, ptr(d), n, ptr(ct)); eb = lib.HUF_compress1X_usingCTable(ptr(ob), n + 256, ptr(d), n, ptr(ct))
         assert ea == eb and bytes(oa[:ea]) == bytes(ob[:eb])
+
+
+def test_double_symbol_table_and_decoders():
+    """HUF_readDTableX2 image (a18) word-equal with the reference at maxTableLog 11 and 12, and HUF_decompress4X2/1X2/4X/1X
+    _usingDTable on that image vs the reference, valid and bit-flipped streams"""
+    lib, isref = checker()
+    if not isref:
+        pytest.skip("needs the compiled reference")
+    L = fb.lib()
+    S = C.c_size_t; V = C.c_void_p
+    for M in (L, lib):
+        for n_, a_ in (("HUF_readDTableX2", [V, V, S]), ("HUF_decompress4X2_usingDTable", [V, S, V, S, V]), ("HUF_decompress1X2_usingDTable", [V, S, V, S, V]),
+                       ("HUF_decompress4X_usingDTable", [V, S, V, S, V]), ("HUF_decompress1X_usingDTable", [V, S, V, S, V]),
+                       ("HUF_compress4X_usingCTable", [V, S, V, S, V]), ("HUF_compress1X_usingCTable", [V, S, V, S, V]),
+                       ("HUF_buildCTable", [V, V, U, U]), ("HUF_writeCTable", [V, S, V, U, U]), ("HIST_count", [V, V, V, S])):
+            f = getattr(M, n_); f.restype = S; f.argtypes = a_
+    lib.HUF_optimalTableLog.argtypes = [U, S, U]
+    rng = np.random.default_rng(313)
+    done = 0
+    for it in range(40):
+        n = int(rng.integers(400, 40000)); d = zoo(rng, n)
+        cnt = (U * 256)(); m = U(255)
+        mx = lib.HIST_count(cnt, C.byref(m), ptr(d), n)
+        if is_error(mx) or mx == n or m.value == 0:
+            continue
+        msv = m.value
+        ct = np.zeros(256, np.uint32)
+        hl = lib.HUF_buildCTable(ptr(ct), cnt, msv, lib.HUF_optimalTableLog(11, n, msv))
+        if is_error(hl):
+            continue
+        hdr = np.zeros(300, np.uint8)
+        hs = lib.HUF_writeCTable(ptr(hdr), 300, ptr(ct), msv, hl)
+        if is_error(hs):
+            continue
+        for Lg in (12, 11):
+            xa = np.zeros(1 + 4096, np.uint32); xb = np.zeros(1 + 4096, np.uint32); xa[0] = xb[0] = Lg * 0x01000001
+            qa = L.HUF_readDTableX2(ptr(xa), ptr(hdr), hs); qb = lib.HUF_readDTableX2(ptr(xb), ptr(hdr), hs)
+            assert qa == qb, (it, Lg, qa, qb)
+            if is_error(qa):
+                continue
+            assert np.array_equal(xa[:1 + (1 << Lg)], xb[:1 + (1 << Lg)]), (it, Lg)
+            for enc, deca, decb in ((lib.HUF_compress4X_usingCTable, L.HUF_decompress4X2_usingDTable, lib.HUF_decompress4X2_usingDTable),
+                                    (lib.HUF_compress1X_usingCTable, L.HUF_decompress1X2_usingDTable, lib.HUF_decompress1X2_usingDTable),
+                                    (lib.HUF_compress4X_usingCTable, L.HUF_decompress4X_usingDTable, lib.HUF_decompress4X_usingDTable),
+                                    (lib.HUF_compress1X_usingCTable, L.HUF_decompress1X_usingDTable, lib.HUF_decompress1X_usingDTable)):
+                cb = np.zeros(n + 600, np.uint8)
+                e = enc(ptr(cb), n + 512, ptr(d), n, ptr(ct))
+                if is_error(e) or e == 0:
+                    continue
+                oa = np.zeros(n + 16, np.uint8); ob = np.zeros(n + 16, np.uint8)
+                ra = deca(ptr(oa), n, ptr(cb), e, ptr(xb)); rb = decb(ptr(ob), n, ptr(cb), e, ptr(xb))
+                assert ra == rb == n and bytes(oa[:n]) == bytes(d[:n]), (it, Lg, ra, rb)
+                bad = cb[:e].copy(); bad[int(rng.integers(6, e))] ^= 1 << int(rng.integers(0, 8))
+                ra = deca(ptr(oa), n, ptr(bad), e, ptr(xb)); rb = decb(ptr(ob), n, ptr(bad), e, ptr(xb))
+                assert is_error(ra) == is_error(rb)
+                done += 1
+    assert done > 20
