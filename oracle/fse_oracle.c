@@ -1082,6 +1082,56 @@ size_t orc_huf_decode4x1(void* dst, size_t dstSize, const void* cSrc, size_t cSi
     return dstSize;
 }
 
+/* a19 (double-symbol)  HUF_decompress1X2/4X2_usingDTable_internal_body (lib/huf_decompress.c:659-862).  A cell yields one
+ * or two symbols per look-up; the last symbol of a stream is taken alone (:668-683). */
+static void huf_finish_stream_x2(u8* out, ptrdiff_t p, ptrdiff_t pEnd, bsrc* b, const u32* cells, unsigned dtLog)   /* :693-720 */
+{
+#define ORC_X2() do { u32 const c_ = cells[src_peek_fast(b, dtLog)]; out[p] = (u8)c_; out[p + 1] = (u8)(c_ >> 8); \
+                      b->used += (c_ >> 16) & 0xFF; p += c_ >> 24; } while (0)
+    while ((src_refill(b) == SRC_MORE) & (p < pEnd - 7)) { ORC_X2(); ORC_X2(); ORC_X2(); ORC_X2(); }
+    while ((src_refill(b) == SRC_MORE) & (p <= pEnd - 2)) ORC_X2();
+    while (p <= pEnd - 2) ORC_X2();
+#undef ORC_X2
+    if (p < pEnd) {
+        u32 const c = cells[src_peek_fast(b, dtLog)];
+        unsigned const nb = (c >> 16) & 0xFF;
+        out[p] = (u8)c;
+        if ((c >> 24) == 1) b->used += nb;
+        else if (b->used < 64) { b->used += nb; if (b->used > 64) b->used = 64; }
+    }
+}
+size_t orc_huf_decode1x2(void* dst, size_t dstSize, const void* cSrc, size_t cSize, const u32* dtable)
+{
+    bsrc b;
+    size_t const e = src_open(&b, cSrc, cSize);
+    if (orc_is_error(e)) return e;
+    huf_finish_stream_x2((u8*)dst, 0, (ptrdiff_t)dstSize, &b, dtable + 1, (dtable[0] >> 16) & 0xFF);
+    if (!src_exhausted(&b)) return ORC_ERROR(ORC_CORRUPT);
+    return dstSize;
+}
+/* Streams are independent: decoding them one after the other yields what the reference's interleaved loop (:797-845) yields
+ * whenever it returns success, and a stream that is not consumed exactly is reported either way (:853-855). */
+size_t orc_huf_decode4x2(void* dst, size_t dstSize, const void* cSrc, size_t cSize, const u32* dtable)
+{
+    const u8* const in = (const u8*)cSrc;
+    u8* const out = (u8*)dst;
+    unsigned const dtLog = (dtable[0] >> 16) & 0xFF;
+    if (cSize < 10) return ORC_ERROR(ORC_CORRUPT);
+    {   size_t const l1 = rd16(in), l2 = rd16(in + 2), l3 = rd16(in + 4);
+        size_t const l4 = cSize - (l1 + l2 + l3 + 6);
+        ptrdiff_t const seg = (ptrdiff_t)((dstSize + 3) / 4), end = (ptrdiff_t)dstSize;
+        size_t const off[4] = { 6, 6 + l1, 6 + l1 + l2, 6 + l1 + l2 + l3 };
+        size_t const len[4] = { l1, l2, l3, l4 };
+        bsrc b[4]; int k;
+        if (l4 > cSize) return ORC_ERROR(ORC_CORRUPT);
+        if (3 * seg > end) return ORC_ERROR(ORC_CORRUPT);             /* same guard as the single-symbol restatement */
+        for (k = 0; k < 4; k++) { size_t const e = src_open(&b[k], in + off[k], len[k]); if (orc_is_error(e)) return e; }
+        for (k = 0; k < 4; k++) huf_finish_stream_x2(out, k * seg, (k < 3) ? (k + 1) * seg : end, &b[k], dtable + 1, dtLog);
+        for (k = 0; k < 4; k++) if (!src_exhausted(&b[k])) return ORC_ERROR(ORC_CORRUPT);
+    }
+    return dstSize;
+}
+
 /* a20  HUF_selectDecoder / HUF_decompress (lib/huf_decompress.c:1001-1081) */
 unsigned orc_huf_select_decoder(size_t dstSize, size_t cSize)
 {

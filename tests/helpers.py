@@ -67,6 +67,7 @@ def load_port():
         _sig(L.orc_huf_read_stats, sz, vp, sz, vp, P(C.c_uint32), P(C.c_uint32), vp, sz)
         _sig(L.orc_huf_read_dtable_x1, sz, vp, vp, sz)
         _sig(L.orc_huf_read_dtable_x2, sz, vp, vp, sz)
+        _sig(L.orc_huf_decode4x2, sz, vp, sz, vp, sz, vp); _sig(L.orc_huf_decode1x2, sz, vp, sz, vp, sz, vp)
         _sig(L.orc_huf_decode4x1, sz, vp, sz, vp, sz, vp)
         _sig(L.orc_huf_decode1x1, sz, vp, sz, vp, sz, vp)
         _sig(L.orc_huf_decompress, sz, vp, sz, vp, sz)
@@ -123,7 +124,9 @@ def load_ref():
         _sig(L.HUF_readStats, sz, vp, sz, vp, P(C.c_uint32), P(C.c_uint32), vp, sz)
         _sig(L.HUF_readDTableX1, sz, vp, vp, sz)
         _sig(L.HUF_readDTableX2, sz, vp, vp, sz)
+        _sig(L.HUF_decompress4X2_usingDTable, sz, vp, sz, vp, sz, vp); _sig(L.HUF_decompress1X2_usingDTable, sz, vp, sz, vp, sz, vp)
         _sig(L.HUF_readDTableX2, sz, vp, vp, sz)
+        _sig(L.HUF_decompress4X2_usingDTable, sz, vp, sz, vp, sz, vp); _sig(L.HUF_decompress1X2_usingDTable, sz, vp, sz, vp, sz, vp)
         _sig(L.HUF_decompress4X1_usingDTable, sz, vp, sz, vp, sz, vp)
         _sig(L.HUF_decompress4X2_usingDTable, sz, vp, sz, vp, sz, vp)
         _sig(L.HUF_decompress4X_usingDTable, sz, vp, sz, vp, sz, vp)

@@ -296,6 +296,16 @@ def test_huf_tables():
                 oa = np.zeros(n, np.uint8); ob = np.zeros(n, np.uint8)
                 assert dec_a(ptr(oa), n, ptr(ca), ea, ptr(dA)) == dec_b(ptr(ob), n, ptr(cb), eb, ptr(dB)) == n
                 assert np.array_equal(oa, d) and np.array_equal(ob, d)
+                # the same stream through the double-symbol table and its decoders, valid and bit-flipped
+                x2a, x2b = (port.orc_huf_decode4x2, ref.HUF_decompress4X2_usingDTable) if enc_a is port.orc_huf_encode4x else (port.orc_huf_decode1x2, ref.HUF_decompress1X2_usingDTable)
+                x12 = np.zeros(1 + 4096, np.uint32); x12[0] = 12 * 0x01000001
+                if is_error(ref.HUF_readDTableX2(ptr(x12), ptr(hb), wb)):
+                    continue
+                oa2 = np.zeros(n + 8, np.uint8); ob2 = np.zeros(n + 8, np.uint8)
+                assert x2a(ptr(oa2), n, ptr(ca), ea, ptr(x12)) == x2b(ptr(ob2), n, ptr(cb), eb, ptr(x12)) == n and np.array_equal(oa2[:n], d)
+                bad = ca[:ea].copy(); bad[int(rng.integers(6 if ea > 6 else 0, ea))] ^= 1 << int(rng.integers(0, 8))
+                va = x2a(ptr(oa2), n, ptr(bad), ea, ptr(x12)); vb = x2b(ptr(ob2), n, ptr(bad), ea, ptr(x12))
+                assert is_error(va) == is_error(vb)
 
 
 def test_select_decoder():
