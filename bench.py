@@ -37,6 +37,53 @@ METRIC = "encode+decode GB/s (uncompressed) per GPU on 32 KB blocks; bit-exact v
 CODEC_ID = {"fse": 0, "huf": 1, "u16": 2}
 
 
+class Workload:
+    """One BASELINE.json config: which codec, which generator, which call parameters.
+      huf : configs[1]  probagen P=14%, HUF_compress2(.., 255, 12) / HUF_decompress, slot FSE_compressBound(32768)   (the headline)
+      fse : configs[2]  probagen P=80%, FSE_compress2(.., 255, 12) / FSE_decompress
+      u16 : configs[4]  generateU16(start 240, p 0.50, seed 1), 16384 symbols per block, FSE_compressU16(dst, 32768, .., 0, 12)
+                        (programs/fuzzerU16.c:107-134, programs/bench.c:190-289, lib/fseU16.c:203-329)"""
+    DEFAULT_P = {"huf": 0.14, "fse": 0.80, "u16": 0.50}
+
+    def __init__(self, codec, p):
+        self.codec = codec
+        self.cid = CODEC_ID[codec]
+        self.p = self.DEFAULT_P[codec] if p is None else p
+        self.block = BLOCK
+        self.slot = 32768 if codec == "u16" else SLOT
+        self.msv, self.tl = (0, 12) if codec == "u16" else (255, 12)
+        self.enc_kernels = {"huf": "huf_plan_kernel+huf_emit_kernel", "fse": "fse_encode_cta_kernel", "u16": "fse_encode_cta_kernel<U16>"}[codec]
+        self.dec_kernels = {"huf": "huf_decode_kernel", "fse": "fse_decode_cta_kernel", "u16": "fse_decode_cta_kernel<U16>"}[codec]
+        self.launches_per_step = {"huf": 4, "fse": 2, "u16": 2}[codec]   # huf: plan, emit, decode, x2-fixup sweep
+
+    def describe(self, mib):
+        if self.codec == "u16":
+            return "generateU16 start=240 p=%.2f %d MiB per GPU (16384 16-bit symbols per 32 KB block), FSE-U16 encode+decode, FSE_compressU16(..,0,12)" % (self.p, mib)
+        return "probagen P=%.0f%% %d MiB per GPU, %s encode+decode, 32 KB blocks, (255,12)" % (self.p * 100, mib, "Huff0 4X" if self.codec == "huf" else "FSE")
+
+    def gen_device(self, L, ptr, nbytes, offset_bytes, stream):
+        if self.codec == "u16":
+            return L.FSEB200_genU16(ptr, nbytes // 2, offset_bytes // 2, 240, self.p, 1, stream)
+        return L.FSEB200_probagen(ptr, nbytes, offset_bytes, self.p, stream)
+
+    def gen_host(self, nbytes):
+        import numpy as np
+        port = os.path.join(ROOT, "oracle", "_build", "libfse_oracle.so")
+        if not os.path.exists(port):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+        L = C.CDLL(port)
+        a = np.empty(nbytes, np.uint8)
+        if self.codec == "u16":
+            L.orc_gen_u16.restype = None
+            L.orc_gen_u16.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_double, C.c_uint32]
+            L.orc_gen_u16(a.ctypes.data_as(C.c_void_p), nbytes // 2, 240, self.p, 1)
+        else:
+            L.orc_probagen.restype = None
+            L.orc_probagen.argtypes = [C.c_void_p, C.c_size_t, C.c_double]
+            L.orc_probagen(a.ctypes.data_as(C.c_void_p), nbytes, self.p)
+        return a
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -44,8 +91,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mib", type=int, default=1024, help="uncompressed MiB per GPU (BASELINE config: 1024)")
-    ap.add_argument("--codec", default="huf", choices=["huf", "fse"])
-    ap.add_argument("--p", type=float, default=0.14)
+    ap.add_argument("--codec", default="huf", choices=["huf", "fse", "u16"], help="huf = BASELINE configs[1] (headline), fse = configs[2], u16 = configs[4]")
+    ap.add_argument("--p", type=float, default=None, help="generator probability (default: the config's: huf 0.14, fse 0.80, u16 0.50)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sg", action="store_true", help="skip the separate scatter/decode/gather line at N > 1")
@@ -76,14 +123,14 @@ def load_checker():
     return L, "port"
 
 
-def cpu_roundtrip(L, kind, codec, data, cbuf, cs, out, res, threads):
+def cpu_roundtrip(L, kind, wl, data, cbuf, cs, out, res, threads):
     """one compress + decompress pass of the CPU implementation over `data`; returns (t_comp, t_decomp) seconds"""
     import numpy as np
-    cid = CODEC_ID[codec]
+    cid = wl.cid; SLOT = wl.slot
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     n = len(data)
     if kind == "reference":
-        tc = L.refshim_compress_blocks(cid, p(data), n, BLOCK, p(cbuf), SLOT, p(cs), 255, 12, threads)
+        tc = L.refshim_compress_blocks(cid, p(data), n, BLOCK, p(cbuf), SLOT, p(cs), wl.msv, wl.tl, threads)
         td = L.refshim_decompress_blocks(cid, p(out), p(data), n, BLOCK, p(cbuf), SLOT, p(cs), p(res), threads)
         return tc, td
     nb = (n + BLOCK - 1) // BLOCK
@@ -96,7 +143,7 @@ def cpu_roundtrip(L, kind, codec, data, cbuf, cs, out, res, threads):
         o = b0 * BLOCK; m = min(n, b1 * BLOCK) - o
         if fn_c:
             L.orc_compress_blocks(cid, data[o:].ctypes.data_as(C.c_void_p), m, BLOCK, cbuf[b0 * SLOT:].ctypes.data_as(C.c_void_p), SLOT,
-                                  cs[b0:].ctypes.data_as(C.c_void_p), 255, 12)
+                                  cs[b0:].ctypes.data_as(C.c_void_p), wl.msv, wl.tl)
         else:
             L.orc_decompress_blocks(cid, out[o:].ctypes.data_as(C.c_void_p), data[o:].ctypes.data_as(C.c_void_p), m, BLOCK,
                                     cbuf[b0 * SLOT:].ctypes.data_as(C.c_void_p), SLOT, cs[b0:].ctypes.data_as(C.c_void_p),
@@ -108,17 +155,28 @@ def cpu_roundtrip(L, kind, codec, data, cbuf, cs, out, res, threads):
     return ts[0], ts[1]
 
 
-def cpu_probagen(n, p):
+def compare_all_blocks(codec, g_c, g_cs, w_c, w_cs, slot, nb):
+    """every block: identical return value and identical compressed bytes.  Returns (ok, blocks compared, bytes compared, detail)."""
     import numpy as np
-    port = os.path.join(ROOT, "oracle", "_build", "libfse_oracle.so")
-    if not os.path.exists(port):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
-    L = C.CDLL(port)
-    L.orc_probagen.restype = None
-    L.orc_probagen.argtypes = [C.c_void_p, C.c_size_t, C.c_double]
-    a = np.empty(n, np.uint8)
-    L.orc_probagen(a.ctypes.data_as(C.c_void_p), n, p)
-    return a
+    g_cs = g_cs[:nb]; w_cs = w_cs[:nb]
+    if not np.array_equal(g_cs, w_cs):
+        bad = int(np.nonzero(g_cs != w_cs)[0][0])
+        return False, nb, 0, "return value of block %d: %d vs reference %d" % (bad, int(g_cs[bad]), int(w_cs[bad]))
+    sizes = w_cs.astype(np.int64).copy()
+    sizes[w_cs > np.uint64(1 << 62)] = 0                      # in-band error codes store nothing
+    if codec != "huf":
+        sizes[sizes == 1] = 0                                  # FSE reports RLE as 1 and stores nothing; HUF stores the byte
+    total = 0
+    cols = np.arange(slot, dtype=np.int64)[None, :]
+    for c0 in range(0, nb, 2048):
+        k = min(2048, nb - c0)
+        G = g_c[c0 * slot:(c0 + k) * slot].reshape(k, slot); W = w_c[c0 * slot:(c0 + k) * slot].reshape(k, slot)
+        diff = (G != W) & (cols < sizes[c0:c0 + k, None])
+        if diff.any():
+            r, c = np.argwhere(diff)[0]
+            return False, nb, total, "byte %d of block %d differs" % (int(c), c0 + int(r))
+        total += int(sizes[c0:c0 + k].sum())
+    return True, nb, total, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,25 +252,26 @@ def run_reference(a):
     n = a.mib << 20
     if threads < 16:
         n = min(n, 256 << 20)                                     # bounded sample on small hosts
-    data = cpu_probagen(n, a.p)
+    wl = Workload(a.codec, a.p)
+    SLOT = wl.slot
+    data = wl.gen_host(n)
     nb = (n + BLOCK - 1) // BLOCK
     cbuf = np.zeros(nb * SLOT + 64, np.uint8); cs = np.zeros(nb, np.uint64)
     out = np.zeros(n, np.uint8); res = np.zeros(nb, np.uint64)
     for _ in range(max(a.warmup, 1)):
-        cpu_roundtrip(L, kind, a.codec, data, cbuf, cs, out, res, threads)
+        cpu_roundtrip(L, kind, wl, data, cbuf, cs, out, res, threads)
     assert np.array_equal(out, data)
     tc = td = 0.0
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        x, y = cpu_roundtrip(L, kind, a.codec, data, cbuf, cs, out, res, threads); tc += x; td += y
+        x, y = cpu_roundtrip(L, kind, wl, data, cbuf, cs, out, res, threads); tc += x; td += y
     wall = time.perf_counter() - t0
     val = n * a.steps / (tc + td) / 1e9
-    sample = "%d MiB of probagen P=%.0f%% (%d blocks), all %d host threads, %d steps" % (n >> 20, a.p * 100, nb, threads, a.steps)
+    sample = "%d MiB of the workload's generator stream (%d blocks), all %d host threads, %d steps" % (n >> 20, nb, threads, a.steps)
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(1e3 * (tc + td) / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic (probagen restatement, seed 1)",
-            "config": {"workload": "probagen P=%.0f%% %d MiB per GPU, %s encode+decode, 32 KB blocks, (255,12)" % (a.p * 100, n >> 20, "Huff0 4X" if a.codec == "huf" else "FSE"),
-                       "block_size": BLOCK, "slot": SLOT, "host_threads": threads},
+            "dtype": "u16" if a.codec == "u16" else "u8", "data": "synthetic (restatement of the reference generator, seed 1)",
+            "config": {"workload": wl.describe(n >> 20), "block_size": BLOCK, "slot": SLOT, "host_threads": threads},
             "encode_gbs": round(n * a.steps / tc / 1e9, 3), "decode_gbs": round(n * a.steps / td / 1e9, 3),
             "compressed_ratio": round(float(cs.astype(np.float64).sum()) / n, 5), "wall_s": round(wall, 2),
             "cpu_baseline": {"value": round(val, 3), "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
@@ -243,7 +302,10 @@ def run_b200(a):
             C.CDLL(None).fflush(None)                              # NCCL writes through libc's buffered stdout
             sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
     L = fb.lib()
+    wl = Workload(a.codec, a.p)
+    SLOT = wl.slot
     for nm, args in (("FSEB200_probagen", [C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p]),
+                     ("FSEB200_genU16", [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_double, C.c_uint, C.c_void_p]),
                      ("FSEB200_compress_host", [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint]),
                      ("FSEB200_decompress_host", [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p])):
         f = getattr(L, nm); f.restype = C.c_size_t; f.argtypes = args
@@ -256,12 +318,12 @@ def run_b200(a):
     out = torch.empty(n, dtype=torch.uint8, device=dev)
     res = torch.empty(nb, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    assert L.FSEB200_probagen(src.data_ptr(), n, rank * n, a.p, stream) == 0     # this rank's shard of the generator stream
-    enc = fb.huf_compress_batch if a.codec == "huf" else fb.fse_compress_batch
-    dec = fb.huf_decompress_batch if a.codec == "huf" else fb.fse_decompress_batch
+    assert wl.gen_device(L, src.data_ptr(), n, rank * n, stream) == 0            # this rank's shard of the generator stream
+    enc = {"huf": fb.huf_compress_batch, "fse": fb.fse_compress_batch, "u16": fb.fseu16_compress_batch}[a.codec]
+    dec = {"huf": fb.huf_decompress_batch, "fse": fb.fse_decompress_batch, "u16": fb.fseu16_decompress_batch}[a.codec]
 
     def step():
-        enc(src, BLOCK, SLOT, 255, 12, cbuf=cbuf, csizes=cs)
+        enc(src, BLOCK, SLOT, wl.msv, wl.tl, cbuf=cbuf, csizes=cs)
         dec(cbuf, cs, n, BLOCK, SLOT, out=out, results=res, orig=src)
 
     def barrier():
@@ -272,20 +334,33 @@ def run_b200(a):
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    # ---- parity gate of the run itself: round trip + byte identity against the CPU checker on a sample ----
+    # ---- parity gate of the run itself: round trip on every rank; on rank 0 EVERY block's return value and compressed bytes
+    #      against the CPU checker's output for the same input (the whole shard where the host has the cores for it) ----
     ok_rt = bool(torch.equal(out, src)) and bool((res[:-1] == BLOCK).all())
     csum = int(cs.sum().item())
-    bit_exact = None
+    bit_exact = None; bit_exact_detail = None; ref_pass = None
     if rank == 0:
         try:
             Lc, kind = load_checker()
-            k = min(nb, 256)
-            h = src[:k * BLOCK].cpu().numpy()
-            wc = np.zeros(k * SLOT + 64, np.uint8); wcs = np.zeros(k, np.uint64); wo = np.zeros(k * BLOCK, np.uint8); wr = np.zeros(k, np.uint64)
-            cpu_roundtrip(Lc, kind, a.codec, h, wc, wcs, wo, wr, min(os.cpu_count() or 1, 16))
+            threads = os.cpu_count() or 1
+            k = nb if threads >= 16 else min(nb, (256 << 20) // BLOCK)       # small hosts: bounded sample, said so in the line
+            m = min(n, k * BLOCK)
+            h = src[:m].cpu().numpy()
+            wc = np.zeros(k * SLOT + 64, np.uint8); wcs = np.zeros(k, np.uint64); wo = np.zeros(m, np.uint8); wr = np.zeros(k, np.uint64)
+            tc0, td0 = cpu_roundtrip(Lc, kind, wl, h, wc, wcs, wo, wr, threads)
             g_cs = cs[:k].cpu().numpy().view(np.uint64); g_c = cbuf[:k * SLOT].cpu().numpy()
-            bit_exact = bool(np.array_equal(g_cs, wcs)) and all(
-                np.array_equal(g_c[b * SLOT: b * SLOT + int(wcs[b])], wc[b * SLOT: b * SLOT + int(wcs[b])]) for b in range(k))
+            okb, nblk, nbytes, why = compare_all_blocks(a.codec, g_c, g_cs, wc, wcs, SLOT, k)
+            # and the other direction: the GPU decodes the CHECKER's compressed blocks to the original bytes
+            d_wc = torch.from_numpy(wc).to(dev); d_wcs = torch.from_numpy(wcs.view(np.int64)).to(dev)
+            o2, r2 = dec(d_wc, d_wcs, m, BLOCK, SLOT, orig=src[:m])
+            torch.cuda.synchronize()
+            cross = bool(torch.equal(o2, src[:m]))
+            del d_wc, d_wcs, o2, r2
+            bit_exact = bool(okb and cross and np.array_equal(wo, h))
+            bit_exact_detail = {"blocks_compared": nblk, "compressed_bytes_compared": nbytes, "of_blocks": nb, "checker": kind,
+                                "gpu_decodes_checker_output": cross, "mismatch": why}
+            ref_pass = (Lc, kind, h, wc, wcs, wo, wr, threads, m, k)
+            del g_c
         except Exception as exc:                                   # checker unavailable: say so, do not guess
             bit_exact = "unchecked: %r" % (exc,)
     # ---- timed region: K steps, events on the launching (torch current) stream ----
@@ -298,7 +373,7 @@ def run_b200(a):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(a.steps):
-        ev[i][0].record(); enc(src, BLOCK, SLOT, 255, 12, cbuf=cbuf, csizes=cs)
+        ev[i][0].record(); enc(src, BLOCK, SLOT, wl.msv, wl.tl, cbuf=cbuf, csizes=cs)
         ev[i][1].record(); dec(cbuf, cs, n, BLOCK, SLOT, out=out, results=res, orig=src)
         ev[i][2].record()
     t1.record()
@@ -323,10 +398,10 @@ def run_b200(a):
         h_cs = torch.empty(nb, dtype=torch.int64, pin_memory=True)
         h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         h_res = torch.empty(nb, dtype=torch.int64, pin_memory=True)
-        cid = CODEC_ID[a.codec]
+        cid = wl.cid
 
         def host_step():
-            r1 = L.FSEB200_compress_host(cid, h_c.data_ptr(), SLOT, h_cs.data_ptr(), h_src.data_ptr(), n, BLOCK, 255, 12)
+            r1 = L.FSEB200_compress_host(cid, h_c.data_ptr(), SLOT, h_cs.data_ptr(), h_src.data_ptr(), n, BLOCK, wl.msv, wl.tl)
             r2 = L.FSEB200_decompress_host(cid, h_out.data_ptr(), n, BLOCK, h_c.data_ptr(), SLOT, h_cs.data_ptr(), h_res.data_ptr(), h_src.data_ptr())
             assert r1 == 0 and r2 == 0
         host_step(); host_step()
@@ -399,7 +474,7 @@ def run_b200(a):
     # ---- roofline of the dominant kernel (algorithmic bytes: S + C each way) ----
     peak, peak_src = measured_peak()
     alg = n + csum
-    kern = {"huf_plan_kernel+huf_emit_kernel" if a.codec == "huf" else "fse_encode_kernel": enc_ms, "huf_decode_kernel" if a.codec == "huf" else "fse_decode_kernel": dec_ms}
+    kern = {wl.enc_kernels: enc_ms, wl.dec_kernels: dec_ms}
     dom = max(kern, key=kern.get)
     roof = lambda ms: round(alg / (ms * 1e-3) / 1e9, 2)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": roof(kern[dom]), "peak": peak, "unit": "GB/s",
@@ -410,17 +485,14 @@ def run_b200(a):
     cpu = None
     if world == 1 and not a.no_cpu:
         try:
-            Lc, kind = load_checker()
-            threads = os.cpu_count() or 1
-            m = n if threads >= 16 else min(n, 128 << 20)
-            h = src[:m].cpu().numpy(); k = (m + BLOCK - 1) // BLOCK
-            wc = np.zeros(k * SLOT + 64, np.uint8); wcs = np.zeros(k, np.uint64); wo = np.zeros(m, np.uint8); wr = np.zeros(k, np.uint64)
-            cpu_roundtrip(Lc, kind, a.codec, h, wc, wcs, wo, wr, threads)
+            if ref_pass is None:
+                raise RuntimeError("checker unavailable")
+            Lc, kind, h, wc, wcs, wo, wr, threads, m, k = ref_pass
             reps = 3; tc = td = 0.0
             for _ in range(reps):
-                x, y = cpu_roundtrip(Lc, kind, a.codec, h, wc, wcs, wo, wr, threads); tc += x; td += y
+                x, y = cpu_roundtrip(Lc, kind, wl, h, wc, wcs, wo, wr, threads); tc += x; td += y
             one = min(m, 64 << 20)
-            x1, y1 = cpu_roundtrip(Lc, kind, a.codec, h[:one], wc, wcs, wo, wr, 1)
+            x1, y1 = cpu_roundtrip(Lc, kind, wl, h[:one], wc, wcs, wo, wr, 1)
             cpu = {"value": round(m * reps / (tc + td) / 1e9, 3), "unit": "GB/s", "cores": threads, "kind": kind,
                    "sample": "%d MiB of the same input, %d reps, encode %.2f GB/s + decode %.2f GB/s" % (m >> 20, reps, m * reps / tc / 1e9, m * reps / td / 1e9),
                    "single_thread": {"value": round(one / (x1 + y1) / 1e9, 4), "encode_gbs": round(one / x1 / 1e9, 4), "decode_gbs": round(one / y1 / 1e9, 4),
@@ -429,14 +501,13 @@ def run_b200(a):
             cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "unavailable", "sample": repr(exc)}
     line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": round(total_ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic (probagen restatement generated in HBM, seed 1, shard = rank * size)",
-            "config": {"workload": "probagen P=%.0f%% %d MiB per GPU, %s encode+decode, 32 KB blocks, (255,12)" % (a.p * 100, a.mib, "Huff0 4X" if a.codec == "huf" else "FSE"),
-                       "block_size": BLOCK, "slot": SLOT, "blocks_per_gpu": nb, "l2": "inputs (%d MiB) larger than the 126 MB L2" % a.mib,
+            "dtype": "u16" if a.codec == "u16" else "u8", "data": "synthetic (reference generator restated, generated in HBM, seed 1, shard = rank * size)",
+            "config": {"workload": wl.describe(a.mib), "block_size": BLOCK, "slot": SLOT, "blocks_per_gpu": nb, "l2": "inputs (%d MiB) larger than the 126 MB L2" % a.mib,
                        "sharding": "independent blocks, contiguous shard per rank, no data-path collective"},
             "encode_gbs_per_gpu": round(n / (enc_ms * 1e-3) / 1e9, 2), "decode_gbs_per_gpu": round(n / (dec_ms * 1e-3) / 1e9, 2),
             "per_gpu": round(value / world, 3), "compressed_ratio": round(csum / n, 5),
-            "bit_exact": bit_exact, "roundtrip_ok": ok_rt,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": sg, "gpu_launches": (3 if a.codec == "huf" else 2) * a.steps,
+            "bit_exact": bit_exact, "bit_exact_detail": bit_exact_detail, "roundtrip_ok": ok_rt,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": sg, "gpu_launches": wl.launches_per_step * a.steps,
             "clocks": sampler.summary(wall0, wall1) if sampler else None}
     print(json.dumps(line))
     if dist is not None:

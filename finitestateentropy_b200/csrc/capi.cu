@@ -11,6 +11,7 @@
 // aborts loudly.  Only scalar helpers (bounds, error names, table-log arithmetic) run on the host.
 #include "common.cuh"
 #include "micro.h"
+#include "launch_util.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +34,7 @@ using namespace fseb;
 
 static cudaError_t huf_dec_std(const BatchGeom& g, void* d, const void* c, const u64* cs, u64* r, const void* o, cudaStream_t s) { return launch_huf_decode(g, d, c, cs, r, o, s, 0); }
 static cudaError_t huf_dec_4x1(const BatchGeom& g, void* d, const void* c, const u64* cs, u64* r, const void* o, cudaStream_t s) { return launch_huf_decode(g, d, c, cs, r, o, s, 1); }
+static cudaError_t huf_dec_4x2(const BatchGeom& g, void* d, const void* c, const u64* cs, u64* r, const void* o, cudaStream_t s) { return launch_huf_decode(g, d, c, cs, r, o, s, 3); }
 
 #define FSEB_API extern "C" __attribute__((visibility("default")))
 
@@ -64,7 +66,8 @@ struct Workspace {
         return d[i];
     }
 };
-Workspace& ws() { static Workspace w; return w; }
+// one workspace per device: streams and buffers belong to the device that was current when they were created
+Workspace& ws() { static Workspace w[MAX_DEVICES]; return w[current_device()]; }
 
 BatchGeom geom(size_t total, size_t blockSize, size_t slot)
 {
@@ -144,6 +147,7 @@ struct Micro {
 };
 
 unsigned hibit_h(unsigned v) { unsigned r = 0; while (v >>= 1) r++; return r; }
+constexpr size_t FSE_ONE_BLOCK_MAX = (size_t)1 << 30;                   // same limit as the batch tier (FSEB_DECL_*)
 
 }  // namespace
 
@@ -243,11 +247,17 @@ FSEB_API void FSE_freeDTable(unsigned* dt) { std::free(dt); }
 // tier 2b: one block per call, host pointers
 // ================================================================================================
 FSEB_API size_t FSE_compress2(void* dst, size_t cap, const void* src, size_t n, unsigned msv, unsigned tl)     // lib/fse.h:105
-{ return one_block_compress(launch_fse_encode, dst, cap, src, n, msv, tl, false); }
+{
+    if (n > FSE_ONE_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);         // the kernels index a block with 32 bits
+    return one_block_compress(launch_fse_encode, dst, cap, src, n, msv, tl, false);
+}
 FSEB_API size_t FSE_compress(void* dst, size_t cap, const void* src, size_t n)                                    // lib/fse.h:67 -> (255, 11)
 { return FSE_compress2(dst, cap, src, n, FSE_MAX_SV, FSE_DEF_TLOG); }
 FSEB_API size_t FSE_decompress(void* dst, size_t cap, const void* cSrc, size_t cSize)                             // lib/fse.h:80
-{ return one_block_decompress(launch_fse_decode, dst, cap, cSrc, cSize); }
+{
+    if (cap > FSE_ONE_BLOCK_MAX || cSize > FSE_ONE_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
+    return one_block_decompress(launch_fse_decode, dst, cap, cSrc, cSize);
+}
 
 FSEB_API size_t HUF_compress2(void* dst, size_t cap, const void* src, size_t n, unsigned msv, unsigned tl)      // lib/huf.h:86
 {
@@ -269,22 +279,29 @@ FSEB_API size_t HUF_decompress(void* dst, size_t dstSize, const void* cSrc, size
     if (dstSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);      // kernels are sized for HUF_BLOCKSIZE_MAX (lib/huf.h:72)
     return one_block_decompress(huf_dec_std, dst, dstSize, cSrc, cSrcSize);
 }
-// Both produce identical bytes for valid input; the GPU path has a single decoder.
+// Both regenerate identical bytes for valid input; on malformed input each returns its CPU namesake's verdict (the batch
+// decoder runs the single-symbol rules, huf_x2_fixup.cu re-examines what those reject under the double-symbol rules).
 FSEB_API size_t HUF_decompress4X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                  // lib/huf.h:155
 {
     if (dstSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
     return one_block_decompress(huf_dec_4x1, dst, dstSize, cSrc, cSrcSize);   // never treats the input as raw / RLE (huf_decompress.c:416-449)
 }
-FSEB_API size_t HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize) { return HUF_decompress4X1(dst, dstSize, cSrc, cSrcSize); }
+FSEB_API size_t HUF_decompress4X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                  // lib/huf.h:160
+{
+    if (dstSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
+    return one_block_decompress(huf_dec_4x2, dst, dstSize, cSrc, cSrcSize);
+}
 
 FSEB_API size_t FSE_compressU16(void* dst, size_t cap, const unsigned short* src, size_t n, unsigned msv, unsigned tl)   // lib/fseU16.h:75
 {
     if (n <= 1) return n;
+    if (n > FSE_ONE_BLOCK_MAX / 2) return (size_t)err(E_SRC_WRONG);
     return one_block_compress(launch_fseu16_encode, dst, cap, src, n * 2, msv, tl, false);
 }
 FSEB_API size_t FSE_decompressU16(unsigned short* dst, size_t cap, const void* cSrc, size_t cSize)                 // lib/fseU16.h:79
 {
     if (cSize < 2) return (size_t)err(E_SRC_WRONG);
+    if (cap > FSE_ONE_BLOCK_MAX / 2 || cSize > FSE_ONE_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
     size_t const r = one_block_decompress(launch_fseu16_decode, dst, cap * 2, cSrc, cSize);
     return FSE_isError(r) ? r : r / 2;
 }
@@ -477,6 +494,16 @@ FSEB_API size_t FSE_buildDTable_raw(unsigned* dt, unsigned nbBits)
 namespace {
 constexpr size_t MICRO_MAX = (size_t)1 << 24;                           // single-call payloads above 16 MiB are refused (use the batch tier)
 size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
+// A caller's HUF_CElt table has HUF_CTABLE_SIZE_U32(maxSymbolValue) = maxSymbolValue+1 cells (lib/huf.h:136-139) and nothing tells
+// us maxSymbolValue: read only the cells the payload can index (up to its largest byte) and hand the device a zero-padded 256-cell image.
+void ctable_image(unsigned (&full)[256], const unsigned* CTable, const void* src, size_t srcSize)
+{
+    unsigned top = 0;
+    const unsigned char* const p = (const unsigned char*)src;
+    for (size_t i = 0; i < srcSize; i++) top = p[i] > top ? p[i] : top;
+    std::memset(full, 0, sizeof(full));
+    std::memcpy(full, CTable, ((size_t)top + 1) * sizeof(unsigned));
+}
 }
 FSEB_API size_t FSE_compress_usingCTable(void* dst, size_t dstSize, const void* src, size_t srcSize, const unsigned* ct)   // lib/fse.h:222
 {
@@ -511,7 +538,8 @@ FSEB_API size_t HUF_compress4X_usingCTable(void* dst, size_t dstSize, const void
     size_t const cap = dstSize < 2 * srcSize + 64 ? dstSize : 2 * srcSize + 64;
     size_t const inOff = 4096, outOff = inOff + al16(srcSize + 16);
     Micro m(outOff + 5 * al16(cap) + 64);
-    m.up(0, CTable, 256 * sizeof(unsigned)); m.up(inOff, src, srcSize);
+    unsigned full[256]; ctable_image(full, CTable, src, srcSize);
+    m.up(0, full, sizeof(full)); m.up(inOff, src, srcSize);
     u64 const r = m.run(MOP_HUF_ENCODE4X_CT, srcSize, cap, inOff, outOff);
     if (!is_err(r) && r) m.down(dst, outOff, (size_t)r);
     return (size_t)r;
@@ -563,7 +591,8 @@ FSEB_API size_t HUF_compress1X_usingCTable(void* dst, size_t dstSize, const void
     size_t const cap = dstSize < 2 * srcSize + 64 ? dstSize : 2 * srcSize + 64;
     size_t const inOff = 4096, outOff = inOff + al16(srcSize + 16);
     Micro m(outOff + cap + 64);
-    m.up(0, CTable, 256 * sizeof(unsigned)); m.up(inOff, src, srcSize);
+    unsigned full[256]; ctable_image(full, CTable, src, srcSize);
+    m.up(0, full, sizeof(full)); m.up(inOff, src, srcSize);
     u64 const r = m.run(MOP_HUF_ENCODE1X_CT, srcSize, cap, inOff, outOff);
     if (!is_err(r) && r) m.down(dst, outOff, (size_t)r);
     return (size_t)r;
@@ -705,7 +734,7 @@ struct HostPipe {
         if (s > capS) { for (int i = 0; i < NS; i++) { if (dS[i]) CK(cudaFree(dS[i])); CK(cudaMalloc(&dS[i], 2 * s * sizeof(u64))); } capS = s; }
     }
 };
-HostPipe& pipe() { static HostPipe p; return p; }
+HostPipe& pipe() { static HostPipe p[MAX_DEVICES]; return p[current_device()]; }
 const size_t CHUNK_BLOCKS = 2048;                                     // 64 MiB of 32 KB blocks per chunk
 }
 
@@ -713,6 +742,7 @@ FSEB_API size_t FSEB200_compress_host(int codec, void* hCBuf, size_t slot, size_
                                       size_t blockSize, unsigned maxSymbolValue, unsigned tableLog)
 {
     if (blockSize == 0 || slot > 0xFFFFFFFFull || codec < 0 || codec > 2) return (size_t)err(E_SRC_WRONG);
+    if (blockSize > (codec == 1 ? (size_t)HUF_BLOCK_MAX : FSE_ONE_BLOCK_MAX)) return (size_t)err(E_SRC_WRONG);
     enc_fn const fn = codec == 0 ? launch_fse_encode : codec == 1 ? launch_huf_encode : launch_fseu16_encode;
     HostPipe& P = pipe();
     std::lock_guard<std::mutex> lock(P.mu);
@@ -755,6 +785,7 @@ FSEB_API size_t FSEB200_decompress_host(int codec, void* hDst, size_t dstTotal, 
                                         const size_t* hCSizes, size_t* hResults, const void* hOrig)
 {
     if (blockSize == 0 || slot > 0xFFFFFFFFull || codec < 0 || codec > 2) return (size_t)err(E_SRC_WRONG);
+    if (blockSize > (codec == 1 ? (size_t)HUF_BLOCK_MAX : FSE_ONE_BLOCK_MAX)) return (size_t)err(E_SRC_WRONG);
     dec_fn const fn = codec == 0 ? launch_fse_decode : codec == 1 ? huf_dec_std : launch_fseu16_decode;
     HostPipe& P = pipe();
     std::lock_guard<std::mutex> lock(P.mu);

@@ -27,6 +27,10 @@ constexpr unsigned FSE_MIN_TLOG = 5, FSE_MAX_TLOG = 12, FSE_DEF_TLOG = 11, FSE_A
 constexpr unsigned HUF_MAX_TLOG = 12, HUF_DEF_TLOG = 11, HUF_MAX_SV = 255, HUF_BLOCK_MAX = 128 * 1024;
 constexpr unsigned U16_MAX_SV = 286, U16_MAX_TLOG = 13, U16_DEF_TLOG = 12;
 
+// Transient per-block result of the batch Huff0 decoder: "rejected by the single-symbol end-of-stream rule, to be re-examined
+// under the double-symbol decoder's rules" (huf_x2_fixup.cu replaces it before the call returns).  Neither a size nor an error code.
+constexpr u64 HUF_X2_PENDING = 0x8000000000000004ull;
+
 __device__ __forceinline__ unsigned hibit(unsigned v) { return 31u - (unsigned)__clz((int)v); }   // v != 0
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 

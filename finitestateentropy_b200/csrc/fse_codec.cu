@@ -21,6 +21,7 @@
 //   fse_encode_kernel      warp per block; takes the ragged last block and unaligned geometries
 #include <cstdlib>
 #include "common.cuh"
+#include "launch_util.cuh"
 #include "fse_dev.cuh"
 #include "bitsrc_dev.cuh"
 
@@ -950,12 +951,9 @@ static cudaError_t launch_dec(const BatchGeom& g, void* dst, const void* cbuf, c
 {
     if (g.nBlocks == 0) return cudaSuccess;
     size_t const smemCta = sizeof(typename fsek::DecCta<WIDE>::Smem);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t const e = cudaFuncSetAttribute(fsek::fse_decode_cta_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCta);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemOptIn optin;                                          // per device: the attribute belongs to the current device
+    {   cudaError_t const e = optin.ensure(fsek::fse_decode_cta_kernel<WIDE>, current_device(), (int)smemCta);
+        if (e != cudaSuccess) return e; }
     unsigned const DK = fsek::DecCta<WIDE>::DK;
     unsigned const grid = (g.nBlocks + DK - 1) / DK;
     fsek::fse_decode_cta_kernel<WIDE><<<grid, fsek::DTHREADS, smemCta, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig);
@@ -965,12 +963,9 @@ template <bool WIDE, int EK>
 static cudaError_t launch_enc_cta(const BatchGeom& g, u32 nFast, void* cbuf, u64* csizes, const void* src, unsigned msv, unsigned tlog, cudaStream_t stream)
 {
     size_t const smemCta = sizeof(typename fsek::EncCta<WIDE, EK>::Smem);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t const e = cudaFuncSetAttribute(fsek::fse_encode_cta_kernel<WIDE, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCta);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemOptIn optin;
+    {   cudaError_t const e = optin.ensure(fsek::fse_encode_cta_kernel<WIDE, EK>, current_device(), (int)smemCta);
+        if (e != cudaSuccess) return e; }
     unsigned const grid = (nFast + EK - 1) / EK;
     fsek::fse_encode_cta_kernel<WIDE, EK><<<grid, fsek::ETHREADS, smemCta, stream>>>(g, nFast, (u8*)cbuf, csizes, (const u8*)src, msv, tlog);
     return cudaGetLastError();
@@ -980,15 +975,10 @@ static cudaError_t launch_enc(const BatchGeom& g, void* cbuf, u64* csizes, const
 {
     if (g.nBlocks == 0) return cudaSuccess;
     size_t const smem = sizeof(fsek::EncWarp<WIDE>) * fsek::WARPS;
-    static bool configured = false;
-    static int ek = 16;
-    if (!configured) {
-        cudaError_t const e = cudaFuncSetAttribute(fsek::fse_encode_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        const char* const v = getenv("FSEB200_ENC_EK");             // tuning knob: blocks per CTA of the chain-warp kernel (16 or 8)
-        if (v && atoi(v) == 8) ek = 8;
-        configured = true;
-    }
+    static SmemOptIn optin;
+    {   cudaError_t const e = optin.ensure(fsek::fse_encode_kernel<WIDE>, current_device(), (int)smem);
+        if (e != cudaSuccess) return e; }
+    static int const ek = [] { const char* const v = getenv("FSEB200_ENC_EK"); return (v && atoi(v) == 8) ? 8 : 16; }();   // tuning knob: blocks per CTA of the chain-warp kernel
     // full, aligned blocks go to the chain-warp kernel; a ragged last block or an odd geometry to the warp-per-block kernel
     u64 const nFull = g.total / g.blockSize;
     bool const fast = g.blockSize >= 64 && g.blockSize % 64 == 0 && (reinterpret_cast<u64>(src) & 15) == 0;

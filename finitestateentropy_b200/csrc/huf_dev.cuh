@@ -10,6 +10,22 @@
 
 namespace fseb {
 
+// HUF_selectDecoder (lib/huf_decompress.c:1001-1051): 1 = the reference decodes this block with its double-symbol decoder.
+__device__ inline u32 d_huf_select_decoder(u64 dstSize, u64 cSrcSize)
+{
+    const u16 cost[16][4] = {
+        {0, 0, 1, 1}, {0, 0, 1, 1}, {38, 130, 1313, 74}, {448, 128, 1353, 74}, {556, 128, 1353, 74},
+        {714, 128, 1418, 74}, {883, 128, 1437, 74}, {897, 128, 1515, 75}, {926, 128, 1613, 75},
+        {947, 128, 1729, 77}, {1107, 128, 2083, 81}, {1177, 128, 2379, 87}, {1242, 128, 2415, 93},
+        {1349, 128, 2644, 106}, {1455, 128, 2422, 124}, {722, 128, 1891, 145} };
+    u32 const q = (cSrcSize >= dstSize) ? 15u : (u32)(cSrcSize * 16 / dstSize);
+    u32 const d256 = (u32)(dstSize >> 8);
+    u32 const t0 = cost[q][0] + cost[q][1] * d256;
+    u32 t1 = cost[q][2] + cost[q][3] * d256;
+    t1 += t1 >> 3;
+    return t1 < t0;
+}
+
 // weights: u8[hwSize] (hwSize = 256), rankStats: u32[13].  Returns header bytes consumed or an error.
 __device__ inline u64 d_huf_read_stats(u8* weights, u64 hwSize, u32* rankStats, u32* nbSymPtr, u32* tlPtr,
                                        const u8* in, u64 srcSize)

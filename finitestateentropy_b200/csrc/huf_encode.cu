@@ -27,6 +27,7 @@
 #include <mutex>
 #include <vector>
 #include "common.cuh"
+#include "launch_util.cuh"
 #include "fse_dev.cuh"
 #include "sink_dev.cuh"
 #include "huf_build_dev.cuh"
@@ -473,12 +474,9 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
     static int serialHeader = -1;
     if (serialHeader < 0) { const char* const v = getenv("FSEB200_HUF_SERIAL_HEADER"); serialHeader = (v && atoi(v) == 1) ? 1 : 0; }   // tuning knob
     {   size_t const smem = sizeof(hufe::PlanWarp) * hufe::PLAN_WARPS;
-        static bool configured = false;
-        if (!configured) {
-            e = cudaFuncSetAttribute(hufe::huf_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
+        static SmemOptIn optin;
+        e = optin.ensure(hufe::huf_plan_kernel, current_device(), (int)smem);
+        if (e != cudaSuccess) return e;
         unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
         hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans, serialHeader);
     }

@@ -8,6 +8,7 @@
 #include "sink_dev.cuh"
 #include "huf_dev.cuh"
 #include "huf_build_dev.cuh"
+#include "huf_x2_dev.cuh"
 #include "micro.h"
 
 namespace fseb {
@@ -229,114 +230,13 @@ __global__ void __launch_bounds__(256) micro_kernel(int op, MicroArgs A, u8* buf
         }
         break; }
     case MOP_HUF_READ_DTABLE_X2: { // HUF_readDTableX2 (huf_decompress.c:551-649): in: bytes @0 (a0), a1 = DTable header word ; out: dtable u32[1+4096] @32768
-        // Cell = { U16 sequence; BYTE nbBits; BYTE length }.  In an index space of width L (= maxTableLog) a symbol of code
-        // length n owns 2^(L-n) cells, weights ascending; where the shortest code still fits behind it, those cells are a
-        // scaled copy of the same layout for the second symbol (second symbols too long to fit leave single-symbol cells).
-        if (tid == 0) {
-            u8* const weights = buf + 4096;
-            u8* const listSym = buf + 8192; u8* const listW = buf + 8192 + 256;
-            u32 rank[17]; u32 nb = 0, tl = 0;
-            u32* const dt = (u32*)(buf + 32768);
-            u32* const cells = dt + 1;
-            u32 const hdr = (u32)A.a[1];
-            u32 const L = hdr & 0xFF;
-            dt[0] = hdr;
-            if (L > HUF_MAX_TLOG) { *ret = err(E_TLOG_TOO_LARGE); break; }
-            u64 const h = d_huf_read_stats(weights, 256, rank, &nb, &tl, buf, A.a[0]);
-            if (is_err(h)) { *ret = h; break; }
-            if (tl > L) { *ret = err(E_TLOG_TOO_LARGE); break; }
-            u32 maxW = tl; while (rank[maxW] == 0) maxW--;
-            u32 listStart[HUF_MAX_TLOG + 2], fill[HUF_MAX_TLOG + 2], first[HUF_MAX_TLOG + 2], next1[HUF_MAX_TLOG + 2], next2[HUF_MAX_TLOG + 2];
-            u32 listSize = 0;
-            for (u32 w = 1; w <= maxW; w++) { listStart[w] = listSize; fill[w] = listSize; listSize += rank[w]; }
-            for (u32 s = 0; s < nb; s++) { u32 const ws = weights[s]; if (ws) { listSym[fill[ws]] = (u8)s; listW[fill[ws]] = (u8)ws; fill[ws]++; } }
-            {   u32 acc = 0;
-                for (u32 w = 1; w <= maxW; w++) { first[w] = acc; next1[w] = acc; acc += rank[w] << (w + (L - tl) - 1); }
-            }
-            u32 const minBits = tl + 1 - maxW;
-            for (u32 i = 0; i < listSize; i++) {
-                u32 const sym = listSym[i], w1 = listW[i], n = tl + 1 - w1;
-                u32 const span = 1u << (L - n);
-                u32* const sub = cells + next1[w1];
-                next1[w1] += span;
-                if (L - n >= minBits) {
-                    int minWeight = (int)n + ((int)tl + 1 - (int)L);
-                    if (minWeight < 1) minWeight = 1;
-                    for (u32 w = 1; w <= maxW; w++) next2[w] = first[w] >> n;
-                    if (minWeight > 1) { u32 const skip = next2[minWeight]; for (u32 u = 0; u < skip; u++) sub[u] = sym | (n << 16) | (1u << 24); }
-                    for (u32 j = listStart[minWeight]; j < listSize; j++) {
-                        u32 const s2 = listSym[j], w2 = listW[j], n2 = tl + 1 - w2;
-                        u32 const len2 = 1u << (L - n - n2);
-                        u32 const cell = ((sym + (s2 << 8)) & 0xFFFF) | ((n + n2) << 16) | (2u << 24);
-                        u32 const at = next2[w2];
-                        for (u32 u = 0; u < len2; u++) sub[at + u] = cell;
-                        next2[w2] += len2;
-                    }
-                } else for (u32 u = 0; u < span; u++) sub[u] = sym | (n << 16) | (1u << 24);
-            }
-            dt[0] = (hdr & 0xFF0000FFu) | (1u << 8) | (L << 16);
-            *ret = h;
-        }
+        if (tid == 0) *ret = d_huf_build_dtable_x2((u32*)(buf + 32768), (u32)A.a[1], buf + 4096, buf + 8192, buf + 8192 + 256, buf, A.a[0]);
         break; }
     case MOP_HUF_DECODE4X2_DT:     // HUF_decompress4X2_usingDTable (huf_decompress.c:749-862): lane k decodes stream k with the double-symbol table
     case MOP_HUF_DECODE1X2_DT: {   // HUF_decompress1X2_usingDTable (:722-747): one stream
         __shared__ u64 s_init2[4]; __shared__ u32 s_done2[4];
-        bool const four = op == MOP_HUF_DECODE4X2_DT;
-        const u32* const dtab = (const u32*)buf;
-        const u32* const cells = dtab + 1;                                           // HUF_DEltX2 { U16 sequence; BYTE nbBits; BYTE length }
-        u32 const dtLog = (dtab[0] >> 16) & 0xFF;
-        const u8* const c = buf + A.a[2]; u8* const out = buf + A.a[3];
-        u64 const cs = A.a[0], n = A.a[1];
-        bool bad = four && cs < 10;
-        u64 l1 = 0, l2 = 0, l3 = 0, l4 = 0;
-        if (four && !bad) {
-            l1 = c[0] | ((u64)c[1] << 8); l2 = c[2] | ((u64)c[3] << 8); l3 = c[4] | ((u64)c[5] << 8);
-            if (l1 + l2 + l3 + 6 > cs) bad = true; else l4 = cs - (l1 + l2 + l3 + 6);
-        }
-        u64 const seg = four ? (n + 3) / 4 : n;
-        if (four && !bad && 3 * seg > n) bad = true;                                 // same guard as the single-symbol path
-        int const nStreams = four ? 4 : 1;
-        if (tid < nStreams) {
-            u64 ie = 0; u32 done = 0;
-            if (!bad) {
-                u64 const lens[4] = { four ? l1 : cs, l2, l3, l4 };
-                u64 off = four ? 6 : 0; for (int k = 0; k < tid; k++) off += lens[k];
-                long long p = (long long)(seg * tid); long long const pe = (four && tid < 3) ? (long long)(seg * (tid + 1)) : (long long)n;
-                BitSrc b;
-                ie = bs_open(b, c + off, lens[tid]);
-                if (!is_err(ie)) {
-                    ie = 0;
-                    auto sym2 = [&]() {                                              // HUF_decodeSymbolX2 :659-666
-                        u32 const cell = cells[bs_peek_fast(b, dtLog)];
-                        out[p] = (u8)cell; out[p + 1] = (u8)(cell >> 8);
-                        b.used += (cell >> 16) & 0xFF; p += cell >> 24;
-                    };
-                    while ((bs_refill(b) == SRC_MORE) & (p < pe - 7)) { sym2(); sym2(); sym2(); sym2(); }   // HUF_decodeStreamX2 :693-720
-                    while ((bs_refill(b) == SRC_MORE) & (p <= pe - 2)) sym2();
-                    while (p <= pe - 2) sym2();
-                    if (p < pe) {                                                    // HUF_decodeLastSymbolX2 :668-683
-                        u32 const cell = cells[bs_peek_fast(b, dtLog)];
-                        u32 const nbb = (cell >> 16) & 0xFF;
-                        out[p++] = (u8)cell;
-                        if ((cell >> 24) == 1) b.used += nbb;
-                        else if (b.used < 64) { b.used += nbb; if (b.used > 64) b.used = 64; }
-                    }
-                    done = bs_exhausted(b) ? 1u : 0u;
-                }
-            }
-            s_init2[tid] = ie; s_done2[tid] = done;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            u64 r = n;
-            if (bad) r = err(E_CORRUPT);
-            else {
-                bool initFailed = false; u32 all = 1;
-                for (int k = 0; k < nStreams; k++) { if (!initFailed && is_err(s_init2[k])) { r = s_init2[k]; initFailed = true; } all &= s_done2[k]; }
-                if (!initFailed && !all) r = err(E_CORRUPT);
-            }
-            *ret = r;
-        }
+        u64 const r = cta_huf_decode_x2(op == MOP_HUF_DECODE4X2_DT, (const u32*)buf, buf + A.a[2], A.a[0], buf + A.a[3], A.a[1], s_init2, s_done2);
+        if (tid == 0) *ret = r;
         break; }
     default: if (tid == 0) *ret = err(E_GENERIC);
     }

@@ -7,9 +7,6 @@
  * (oracle/_ref), tests/golden/ and SURVEY.md section 6.3 by tests/test_oracle_vs_ref.py.
  *
  * Known, documented deviations (all on inputs the reference itself treats as unsupported):
- *   - orc_huf_decompress always decodes with the single-symbol table (X1); the reference picks
- *     X1 or X2 by a CPU timing heuristic (lib/huf_decompress.c:1029-1051), both regenerate the
- *     same bytes for a valid stream.
  *   - orc_huf_decode4x1 refuses dstSize < 6 (the reference would write 1 byte out of bounds,
  *     lib/huf_decompress.c:291-296,344-347); HUF_compress never emits such blocks (:565).
  *   - orc_fse_compress2 builds its CTable in private storage.  FSE_compress_wksp sizes CTable+scratch
@@ -1148,19 +1145,40 @@ unsigned orc_huf_select_decoder(size_t dstSize, size_t cSize)
     return t1 < t0;
 }
 
-size_t orc_huf_decompress(void* dst, size_t dstSize, const void* cSrc, size_t cSize)
+/* HUF_decompress4X1 / HUF_decompress4X2 (lib/huf_decompress.c:416-449,917-952): header + payload with a fixed decoder */
+size_t orc_huf_decompress4x1(void* dst, size_t dstSize, const void* cSrc, size_t cSize)
 {
     u32 dtable[1 + 4096];
     size_t h;
-    if (dstSize == 0) return ORC_ERROR(ORC_DST_TOO_SMALL);
-    if (cSize > dstSize) return ORC_ERROR(ORC_CORRUPT);
-    if (cSize == dstSize) { memcpy(dst, cSrc, dstSize); return dstSize; }
-    if (cSize == 1) { memset(dst, *(const u8*)cSrc, dstSize); return dstSize; }
     dtable[0] = (HUF_MAX_TLOG - 1) * 0x01000001u;
     h = orc_huf_read_dtable_x1(dtable, cSrc, cSize);
     if (orc_is_error(h)) return h;
     if (h >= cSize) return ORC_ERROR(ORC_SRC_WRONG);
     return orc_huf_decode4x1(dst, dstSize, (const u8*)cSrc + h, cSize - h, dtable);
+}
+
+size_t orc_huf_decompress4x2(void* dst, size_t dstSize, const void* cSrc, size_t cSize)
+{
+    u32 dtable[1 + 4096];
+    size_t h;
+    dtable[0] = HUF_MAX_TLOG * 0x01000001u;
+    h = orc_huf_read_dtable_x2(dtable, cSrc, cSize);
+    if (orc_is_error(h)) return h;
+    if (h >= cSize) return ORC_ERROR(ORC_SRC_WRONG);
+    return orc_huf_decode4x2(dst, dstSize, (const u8*)cSrc + h, cSize - h, dtable);
+}
+
+/* HUF_decompress (lib/huf_decompress.c:1056-1081): raw / RLE, then the decoder HUF_selectDecoder picks.  Both decoders
+ * regenerate the same bytes for a valid stream; on malformed streams the double-symbol decoder accepts some the
+ * single-symbol one rejects (HUF_decodeLastSymbolX2 clamps the bit count), so the choice is part of the verdict. */
+size_t orc_huf_decompress(void* dst, size_t dstSize, const void* cSrc, size_t cSize)
+{
+    if (dstSize == 0) return ORC_ERROR(ORC_DST_TOO_SMALL);
+    if (cSize > dstSize) return ORC_ERROR(ORC_CORRUPT);
+    if (cSize == dstSize) { memcpy(dst, cSrc, dstSize); return dstSize; }
+    if (cSize == 1) { memset(dst, *(const u8*)cSrc, dstSize); return dstSize; }
+    return orc_huf_select_decoder(dstSize, cSize) ? orc_huf_decompress4x2(dst, dstSize, cSrc, cSize)
+                                                  : orc_huf_decompress4x1(dst, dstSize, cSrc, cSize);
 }
 
 /* ==========================================================================================

@@ -68,6 +68,8 @@ size_t orc_huf_decode4x1(void* dst, size_t dstSize, const void* cSrc, size_t cSr
 size_t orc_huf_decode1x1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const uint32_t* dtable);
 size_t orc_huf_decode4x2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const uint32_t* dtable);   /* double-symbol table */
 size_t orc_huf_decode1x2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const uint32_t* dtable);
+size_t orc_huf_decompress4x1(void* dst, size_t dstSize, const void* cSrc, size_t cSize);
+size_t orc_huf_decompress4x2(void* dst, size_t dstSize, const void* cSrc, size_t cSize);
 size_t orc_huf_decompress(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
 unsigned orc_huf_select_decoder(size_t dstSize, size_t cSrcSize);
 

@@ -71,6 +71,7 @@ def load_port():
         _sig(L.orc_huf_decode4x1, sz, vp, sz, vp, sz, vp)
         _sig(L.orc_huf_decode1x1, sz, vp, sz, vp, sz, vp)
         _sig(L.orc_huf_decompress, sz, vp, sz, vp, sz)
+        _sig(L.orc_huf_decompress4x1, sz, vp, sz, vp, sz); _sig(L.orc_huf_decompress4x2, sz, vp, sz, vp, sz)
         _sig(L.orc_huf_select_decoder, u, sz, sz)
         _sig(L.orc_probagen, None, vp, sz, C.c_double)
         _sig(L.orc_gen_u16, None, vp, sz, u, C.c_double, C.c_uint32)
