@@ -36,6 +36,13 @@ def build_lib(force=False, verbose=False):
 def build_oracles():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "fuzzers"])   # the reference's fuzzers linked against OUR library
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "cli"])       # the reference's file tool (frame-format checker)
+
+
+def build_programs():
+    """host programs over the C-ABI (programs/Makefile): bench_gpu, fse_b200_file"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "programs"), "all"])
 
 
 if __name__ == "__main__":

@@ -25,6 +25,7 @@ cudaError_t launch_fse_encode(const BatchGeom&, void*, u64*, const void*, unsign
 cudaError_t launch_fseu16_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t);
 cudaError_t launch_fseu16_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
 cudaError_t launch_hist(const void*, u64, u32, u32*, u64*, cudaStream_t);
+cudaError_t launch_hist16(const void*, u64, u32, u32*, u64*, cudaStream_t);
 cudaError_t launch_micro(int, const MicroArgs&, void*, u64*, cudaStream_t);
 cudaError_t launch_gen8(void*, u64, u64, const void*, u32, cudaStream_t);
 cudaError_t launch_gen16(void*, u64, u64, const void*, u32, cudaStream_t);
@@ -338,6 +339,28 @@ FSEB_API size_t HIST_count_wksp(unsigned* count, unsigned* msvPtr, const void* s
 }
 FSEB_API size_t HIST_countFast_wksp(unsigned* count, unsigned* msvPtr, const void* src, size_t n, void* wksp, size_t wkspSize)
 { return HIST_count_wksp(count, msvPtr, src, n, wksp, wkspSize); }
+
+FSEB_API size_t FSE_countU16(unsigned* count, unsigned* msvPtr, const unsigned short* src, size_t n)                   // lib/fseU16.c:121-145
+{
+    unsigned const declared = *msvPtr > 65535u ? 65535u : *msvPtr;       // a 16-bit symbol cannot exceed it
+    if (n > FSE_ONE_BLOCK_MAX / 2) return (size_t)err(E_SRC_WRONG);
+    Workspace& w = ws();
+    std::lock_guard<std::mutex> lock(w.mu);
+    unsigned char* dS = (unsigned char*)w.get(0, n * 2);
+    u32* dOut = (u32*)w.get(1, ((size_t)declared + 2) * sizeof(u32));
+    u64* dR = (u64*)w.get(2, 2 * sizeof(u64));
+    u64 r = 0; u32 top = 0;
+    if (n) CK(cudaMemcpyAsync(dS, src, n * 2, cudaMemcpyHostToDevice, w.stream));
+    CK(launch_hist16(dS, n, declared, dOut, dR, w.stream));
+    CK(cudaMemcpyAsync(&r, dR, sizeof(r), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaMemcpyAsync(count, dOut, ((size_t)declared + 1) * sizeof(u32), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaMemcpyAsync(&top, dOut + declared + 1, sizeof(top), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    if (*msvPtr > declared) std::memset(count + declared + 1, 0, ((size_t)*msvPtr - declared) * sizeof(unsigned));
+    if (is_err(r)) return (size_t)r;
+    *msvPtr = top;
+    return (size_t)r;
+}
 
 FSEB_API size_t FSE_normalizeCount(short* norm, unsigned tl, const unsigned* count, size_t total, unsigned msv)   // lib/fse.h:147
 {

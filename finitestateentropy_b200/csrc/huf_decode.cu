@@ -29,7 +29,7 @@
 //   * stream ring: 8 words per lane, word-interleaved ring[slot][tid] (bank = lane: conflict-free for any 32
 //     cursors).  The lane tops it up itself with one 16-byte global load per 4 words, issued one top-up ahead into
 //     registers (the load is in flight across ~16 symbols of work, nothing waits on it);
-//   * output: 16 symbols are packed into one 16-byte store per lane;
+//   * output: 32 symbols are packed into one 32-byte store per lane (STG.256: a whole sector per store);
 //   * blocks whose best table exceeds the row budget ("hard", e.g. near-flat 256-symbol alphabets), unaligned
 //     segments and ragged tails take a per-symbol loop (canonical-code search for hard blocks).
 #include "common.cuh"
@@ -325,14 +325,17 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     } while (0)
 
     u32 pos = 0;
-    bool const fastOk = go && !hardBlk && ((reinterpret_cast<u64>(outp) & 15) == 0);
+    // 32 symbols -> ONE 32-byte store per lane (STG.256).  Every lane writes its own stream, so stores cannot coalesce across
+    // lanes; what matters is that each one covers a whole 32-byte sector: measured on this access pattern (scripts/ubench/
+    // scatter.cu) 16-byte stores cost 0.78 ms per GiB on their own -- partial-sector writes -- against 0.23 ms for 32-byte ones.
+    bool const fastOk = go && !hardBlk && ((reinterpret_cast<u64>(outp) & 31) == 0);
     if (fastOk) {
-        u32 const nIter = segLen >> 4;
-        for (u32 it = 0; it < nIter; it++) {             // 16 symbols -> one 16-byte store per lane
-            u32 o[4];
+        u32 const nIter = segLen >> 5;
+        for (u32 it = 0; it < nIter; it++) {
+            u32 o[8];
             #pragma unroll
-            for (int h = 0; h < 4; h++) {
-                if (h == 0) top_up(4); else if (h == 2) top_up(3);   // every 8 symbols
+            for (int h = 0; h < 8; h++) {
+                if ((h & 3) == 0) top_up(4); else if ((h & 3) == 2) top_up(3);   // every 8 symbols
                 u32 e0, e1, e2, e3, hi1;
                 HUFD_LOOKUP(e0, hi); hi1 = __funnelshift_l(lo, hi, e0); HUFD_LOOKUP(e1, hi1);
                 r += e0 + e1;
@@ -342,8 +345,9 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
                 HUFD_ADVANCE();
                 o[h] = __byte_perm(e0 | (e1 << 16), e2 | (e3 << 16), 0x7531);
             }
-            *reinterpret_cast<uint4*>(outp + pos) = make_uint4(o[0], o[1], o[2], o[3]);
-            pos += 16;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         :: "l"(outp + pos), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            pos += 32;
         }
     }
     // ragged tails, unaligned segments and hard blocks: one symbol at a time

@@ -38,6 +38,29 @@ __global__ void __launch_bounds__(256) hist_kernel(const u8* src, u64 n, u32 dec
     }
 }
 
+// ---- FSE_countU16 (lib/fseU16.c:121-145): histogram of 16-bit symbols, one CTA, counters in global scratch ----
+// out: count u32[declared+1], then out[declared+1] = largest present symbol.  ret: largest count, 0 for an empty input, or
+// maxSymbolValue_tooSmall if a symbol exceeds `declared` (the reference stops at the first such symbol; the counts it leaves
+// behind are unspecified, ours are zeros).
+__global__ void __launch_bounds__(256) hist16_kernel(const u16* src, u64 n, u32 declared, u32* out, u64* ret)
+{
+    __shared__ u32 s_bad, s_top, s_best;
+    int const tid = threadIdx.x;
+    for (u32 i = tid; i <= declared + 1; i += 256) out[i] = 0;
+    if (tid == 0) { s_bad = 0; s_top = 0; s_best = 0; }
+    __syncthreads();
+    u32 bad = 0;
+    for (u64 i = tid; i < n; i += 256) { u32 const v = src[i]; if (v > declared) bad = 1; else atomicAdd(&out[v], 1u); }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (s_bad) { for (u32 i = tid; i <= declared; i += 256) out[i] = 0; if (tid == 0) *ret = err(E_MSV_TOO_SMALL); return; }
+    u32 top = 0, best = 0;
+    for (u32 i = tid; i <= declared; i += 256) { u32 const c = out[i]; if (c) { top = i; best = c > best ? c : best; } }
+    atomicMax(&s_top, top); atomicMax(&s_best, best);
+    __syncthreads();
+    if (tid == 0) { out[declared + 1] = n ? s_top : 0; *ret = n ? s_best : 0; }
+}
+
 // ---- everything O(alphabet)/O(table): one kernel, op-code dispatched ----
 // buf layout is op specific (see capi.cu); a[] carries scalars.
 __global__ void __launch_bounds__(256) micro_kernel(int op, MicroArgs A, u8* buf, u64* ret)
@@ -244,6 +267,8 @@ __global__ void __launch_bounds__(256) micro_kernel(int op, MicroArgs A, u8* buf
 
 cudaError_t launch_hist(const void* src, u64 n, u32 declared, u32* out, u64* ret, cudaStream_t s)
 { hist_kernel<<<1, 256, 0, s>>>((const u8*)src, n, declared, out, ret); return cudaGetLastError(); }
+cudaError_t launch_hist16(const void* src, u64 n, u32 declared, u32* out, u64* ret, cudaStream_t s)
+{ hist16_kernel<<<1, 256, 0, s>>>((const u16*)src, n, declared, out, ret); return cudaGetLastError(); }
 cudaError_t launch_micro(int op, const MicroArgs& A, void* buf, u64* ret, cudaStream_t s)
 { micro_kernel<<<1, 256, 0, s>>>(op, A, (u8*)buf, ret); return cudaGetLastError(); }
 

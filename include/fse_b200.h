@@ -162,6 +162,9 @@ size_t      HUF_decompress1X1_usingDTable(void* dst, size_t maxDstSize, const vo
 size_t      FSE_compressU16(void* dst, size_t dstCapacity, const unsigned short* src, size_t srcSize,
                             unsigned maxSymbolValue, unsigned tableLog);
 size_t      FSE_decompressU16(unsigned short* dst, size_t dstCapacity, const void* cSrc, size_t cSrcSize);
+/* lib/fseU16.c:121-145 (not in fseU16.h; programs/fuzzerU16.c:257 declares it `extern`): histogram of 16-bit symbols on the GPU.
+ * *maxSymbolValuePtr in: largest symbol `count` has room for; out: largest symbol present.  Returns the largest count. */
+size_t      FSE_countU16(unsigned* count, unsigned* maxSymbolValuePtr, const unsigned short* src, size_t srcSize);
 
 #ifdef __cplusplus
 }
