@@ -206,7 +206,8 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     u32 const seg = (n + 3) / 4;
     u32 segLen = 0;                                  // symbols this lane must produce
     u8* outp = dst + (u64)b * g.blockSize + (u64)strm * seg;
-    u64 chunkTop = 0, sBegin = 0;                    // address just above chunk 0 ; first byte of the stream
+    u64 chunkTop = 0;                                // address just above chunk 0
+    u32 expectBits = 0;                              // stream bits between chunkTop and the first byte of the stream
     u32 c0 = 0;                                      // bits to skip at the top of chunk 0: garbage above the stream + zero padding + end mark
     u32 const tl = fx.tlog[col];
 
@@ -230,10 +231,11 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
                     u8 const last = pay[off + len - 1];
                     if (last == 0) code = (len >= 8) ? E_GENERIC : E_CORRUPT;        // :282-284 / :303-306
                     else {
-                        sBegin = (u64)(pay + off);
+                        u64 const sBegin = (u64)(pay + off);
                         u64 const e = sBegin + len;                                  // one past the last byte
                         chunkTop = ((e - 1) & ~15ull) + 16;
                         c0 = (u32)(8 * (chunkTop - e)) + (8 - hibit(last));
+                        expectBits = (u32)(8 * (chunkTop - sBegin));
                         segLen = (strm < 3) ? seg : n - 3 * seg;
                     }
                 }
@@ -246,20 +248,20 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     if (!go) segLen = 0;
 
     // ---- stream feeder ----
-    // Stream word j (j = 0 is the word just below chunkTop) is the little-endian u32 at chunkTop - 4(j+1); bytes below the
-    // stream start read as 0 (the reference's reader pads the same way).  Chunk q = words 4q..4q+3 = one aligned 16 bytes.
+    // Stream word j (j = 0 is the word just below chunkTop) is the little-endian u32 at chunkTop - 4(j+1); chunk q = words
+    // 4q..4q+3 = one aligned 16 bytes.  Below the first byte of the stream the feeder delivers whatever lies there (the
+    // previous stream, the jump table, the header): the reference pads with zeros instead, but those bits can only be
+    // CONSUMED by a stream that is already over-read -- a code that straddles the stream start decodes, under any padding,
+    // to a length beyond the bits that are left (prefix property) -- so the verdict "consumed == stream bits" is the same,
+    // and a rejected block's bytes are not part of the contract.  That keeps the hot loop to ONE unconditional 16-byte load:
+    // with a second, conditional load path inlined next to it, ptxas shared a scoreboard slot between the two and every
+    // 16 symbols the window shift waited a DRAM round trip for a load it does not depend on (ncu round 2: 13% of samples).
+    // Chunks that would lie below the compressed buffer itself re-read its first 16 bytes (address clamp, never dereferenced
+    // out of bounds).
     u32 const ringLane = (u32)__cvta_generic_to_shared(ringRaw) + tid * 4;      // + slot * (THREADS*4)
-    u32 const fullChunks = go ? (u32)((chunkTop - ((sBegin + 15) & ~15ull)) >> 4) : 0u;   // chunks 0..fullChunks-1 lie entirely inside the stream
-    auto load_word = [&](u32 j) -> u32 {
-        u64 const a = chunkTop - 4ull * (j + 1);
-        if (4ull * (j + 1) > chunkTop - (sBegin & ~3ull)) return 0u;             // entirely below the stream (also guards the address)
-        u32 v = __ldg(reinterpret_cast<const u32*>(a));
-        if (a < sBegin) v &= 0xFFFFFFFFu << (8 * (u32)(sBegin - a));
-        return v;
-    };
+    u32 const qLimit = go ? (u32)((chunkTop - (reinterpret_cast<u64>(cbuf) & ~15ull)) >> 4) - 1u : 0u;   // last chunk at or above the buffer start
     auto load_chunk = [&](u32 q) -> uint4 {                                      // memory order: .x lowest address = word 4q+3
-        if (q < fullChunks) return __ldg(reinterpret_cast<const uint4*>(chunkTop - 16ull * (q + 1)));
-        return make_uint4(load_word(4 * q + 3), load_word(4 * q + 2), load_word(4 * q + 1), load_word(4 * q));
+        return __ldg(reinterpret_cast<const uint4*>(chunkTop - 16ull * (min(q, qLimit) + 1)));
     };
     auto store_chunk = [&](u32 q, uint4 v) {                                     // chunk q -> ring slots (4q .. 4q+3) mod 8
         u32 const a = ringLane + (q & 1) * (4 * THREADS * 4);
@@ -270,16 +272,6 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     u32 ctr = 0;                                      // ring read cursor: (ctr >> 29) = slot of the next word to fetch
     u32 q = 0;                                        // chunk held in P (chunks 0..q-1 are consumed or in the ring)
     uint4 P = make_uint4(0, 0, 0, 0);
-    if (go) {
-        u32 const k0 = c0 >> 5;                       // 0..4
-        r = c0 & 31;
-        w0 = load_word(k0); w1 = load_word(k0 + 1); w2 = load_word(k0 + 2);
-        u32 const q1 = (k0 + 3) >> 2;                 // chunk holding word k0+3, the first one read through the ring
-        store_chunk(q1, load_chunk(q1)); store_chunk(q1 + 1, load_chunk(q1 + 1));
-        ctr = ((k0 + 3) & 7) << 29;
-        q = q1 + 2;
-        P = load_chunk(q);
-    }
     // Words written but not yet fetched: U = 4q - (absolute index of the next word to fetch).  The ring is topped up at two
     // kinds of check, 8 symbols (at most 3 fetched words) apart: the group-start check stores the pending chunk when U <= 4, the
     // mid-group check only when U <= 3.  Induction: U >= 5 after a group-start check, hence >= 2 at the mid-group one and
@@ -288,13 +280,28 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     // check stores: the 16-byte load it issues has 16 symbols of work to land before the next store of this WARP touches
     // the same registers (the scoreboard is per warp, not per lane: a store every 8 symbols exposed the DRAM latency).
     auto unread = [&]() -> u32 { return ((4 * q - (ctr >> 29) - 1) & 7) + 1; };
+    // The load of chunk q is consumed 16 symbols later -- not enough to cover a DRAM round trip under load (ncu: the store of P
+    // waited on it for 16% of all samples) -- so every top-up also asks the L2 for the sector four chunks further down the
+    // stream; by the time the demand load is issued it is an L2 hit, which 16 symbols of decoding do cover.
     auto top_up = [&](u32 threshold) {
         if (unread() <= threshold) {
             store_chunk(q, P);
             q++;
             P = load_chunk(q);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(chunkTop - 16ull * (min(q + 4, qLimit) + 1)));
         }
     };
+
+    if (go) {                                         // chunks 0 and 1 fill the ring, the window words come out of it, chunk 2 follows
+        store_chunk(0, load_chunk(0)); store_chunk(1, load_chunk(1));
+        q = 2; P = load_chunk(2);
+        r = c0 & 31;
+        ctr = (c0 >> 5) << 29;                        // first word of the window: 0..4
+        w0 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); ctr += 1u << 29;
+        w1 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); ctr += 1u << 29;
+        w2 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); ctr += 1u << 29;
+        top_up(4);                                    // 1..5 words unread: bring the ring to >= 5
+    }
 
     // ---- decode ----
     u32 const tblCol = (u32)__cvta_generic_to_shared(tbl) + col * 2;       // + row * 128
@@ -313,14 +320,17 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
         int const y_ = (int)((H) >> shY); \
         E = lds_u16((u32)min(a_, y_) * (G * 2) + tblColD); \
     } while (0)
-    // after a pair of symbols: account the bits, rotate the words when the offset crossed 32, recompute the window
-#define HUFD_ADVANCE() do { \
-        if (r & 32u) { \
-            w0 = w1; w1 = w2; \
-            w2 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); \
-            ctr += 1u << 29; \
-            r -= 32u; \
-        } \
+    // After a pair of symbols: `r` has grown by their bits (it is never reduced: the funnel shifts take it modulo 32 and
+    // bit 5 FLIPS exactly when a 32-bit word has been used up -- a pair is at most 24 bits).  Then the words rotate and the
+    // next one comes out of the ring, all predicated; the window is recomputed from the raw words either way.
+#define HUFD_ADVANCE(ADDED) do { \
+        u32 const rOld_ = r; \
+        r += (ADDED); \
+        u32 const ra_ = ringLane + __umulhi(ctr, RW * THREADS * 4); \
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t" \
+                     "xor.b32 t, %5, %6;\n\tand.b32 t, t, 32;\n\tsetp.ne.u32 p, t, 0;\n\t" \
+                     "@p mov.b32 %0, %1;\n\t@p mov.b32 %1, %2;\n\t@p ld.shared.u32 %2, [%4];\n\t@p add.u32 %3, %3, 0x20000000;\n\t}" \
+                     : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(ctr) : "r"(ra_), "r"(r), "r"(rOld_) : "memory"); \
         hi = __funnelshift_l(w1, w0, r); lo = __funnelshift_l(w2, w1, r); \
     } while (0)
 
@@ -335,14 +345,13 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
             u32 o[8];
             #pragma unroll
             for (int h = 0; h < 8; h++) {
-                if ((h & 3) == 0) top_up(4); else if ((h & 3) == 2) top_up(3);   // every 8 symbols
+                if ((h & 3) == 0) top_up(4);                                     // group start: the common store
+                else if ((h & 3) == 2 && __builtin_expect(__any_sync(__activemask(), unread() <= 3), 0)) top_up(3);   // mid-group: only when a lane ran low (lanes leave this loop at different trip counts: vote among those still in it)
                 u32 e0, e1, e2, e3, hi1;
                 HUFD_LOOKUP(e0, hi); hi1 = __funnelshift_l(lo, hi, e0); HUFD_LOOKUP(e1, hi1);
-                r += e0 + e1;
-                HUFD_ADVANCE();
+                HUFD_ADVANCE(e0 + e1);
                 HUFD_LOOKUP(e2, hi); hi1 = __funnelshift_l(lo, hi, e2); HUFD_LOOKUP(e3, hi1);
-                r += e2 + e3;
-                HUFD_ADVANCE();
+                HUFD_ADVANCE(e2 + e3);
                 o[h] = __byte_perm(e0 | (e1 << 16), e2 | (e3 << 16), 0x7531);
             }
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -366,8 +375,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
             u32 e;
             if (hardBlk) e = parked_cell(hi >> (32 - tl));
             else HUFD_LOOKUP(e, hi);
-            r += e & 0xFF;
-            HUFD_ADVANCE();
+            HUFD_ADVANCE(e & 0xFF);
             outp[pos++] = (u8)(e >> 8);
         }
     }
@@ -378,8 +386,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     if (go) {
         u64 const fetched = 4ull * q - unread();                        // absolute index of the next word to fetch; w0 is word fetched-3
         u64 const consumed = 32ull * (fetched - 3) + (r & 31);
-        u64 const expect = 8ull * (chunkTop - sBegin);
-        if (consumed != expect) atomicMin(&fx.status[col], (u32)(5u << 8 | E_CORRUPT));
+        if (consumed != (u64)expectBits) atomicMin(&fx.status[col], (u32)(5u << 8 | E_CORRUPT));
     }
     __syncthreads();
     if (tid < G) {
