@@ -202,7 +202,9 @@ class ClockSampler:
 
     def start(self):
         self.t.start()
-        time.sleep(0.15)                                           # let the first rows arrive before the timed region opens
+        t0 = time.perf_counter()                                   # nvidia-smi can take a second to print its first row on a cold box
+        while len(self.rows) < 2 and time.perf_counter() - t0 < 5.0:
+            time.sleep(0.05)
 
     def stop(self):
         time.sleep(0.05)

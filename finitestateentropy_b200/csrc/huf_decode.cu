@@ -233,7 +233,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
                     else {
                         u64 const sBegin = (u64)(pay + off);
                         u64 const e = sBegin + len;                                  // one past the last byte
-                        chunkTop = ((e - 1) & ~15ull) + 16;
+                        chunkTop = ((e - 1) & ~31ull) + 32;
                         c0 = (u32)(8 * (chunkTop - e)) + (8 - hibit(last));
                         expectBits = (u32)(8 * (chunkTop - sBegin));
                         segLen = (strm < 3) ? seg : n - 3 * seg;
@@ -259,48 +259,58 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     // Chunks that would lie below the compressed buffer itself re-read its first 16 bytes (address clamp, never dereferenced
     // out of bounds).
     u32 const ringLane = (u32)__cvta_generic_to_shared(ringRaw) + tid * 4;      // + slot * (THREADS*4)
-    u32 const qLimit = go ? (u32)((chunkTop - (reinterpret_cast<u64>(cbuf) & ~15ull)) >> 4) - 1u : 0u;   // last chunk at or above the buffer start
-    auto load_chunk = [&](u32 q) -> uint4 {                                      // memory order: .x lowest address = word 4q+3
-        return __ldg(reinterpret_cast<const uint4*>(chunkTop - 16ull * (min(q, qLimit) + 1)));
-    };
-    auto store_chunk = [&](u32 q, uint4 v) {                                     // chunk q -> ring slots (4q .. 4q+3) mod 8
-        u32 const a = ringLane + (q & 1) * (4 * THREADS * 4);
-        sts_u32(a, v.w); sts_u32(a + THREADS * 4, v.z); sts_u32(a + 2 * THREADS * 4, v.y); sts_u32(a + 3 * THREADS * 4, v.x);
+    // Global loads are 32 bytes (one whole sector, LDG.256) = a PAIR of chunks: the lane's scattered 16-byte loads fetched
+    // every sector twice (nothing survives in an L1 that shares 228 KB with 223 KB of shared memory) and cost twice the LSU
+    // wavefronts.  The pair waits in eight registers; its two chunks enter the ring one after the other.
+    u32 const pLimit = go ? (u32)((chunkTop - (reinterpret_cast<u64>(cbuf) & ~31ull)) >> 5) - 1u : 0u;   // last pair at or above the buffer start
+    u32 m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0;        // pending pair, memory order (m7 = highest address = first consumed)
+    auto load_pair = [&](u32 pr) {
+        u64 const a = chunkTop - 32ull * (min(pr, pLimit) + 1);
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7) : "l"(a));
+        // ... and the L2 is asked for the sector two pairs further down the stream: the demand load above was itself
+        // announced that way, so it is an L2 hit by now -- the 16 symbols until its data is needed cover an L2 round trip,
+        // they did not cover a DRAM one (ncu: the store of the pending chunk waited on it for 16% of all samples).
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(chunkTop - 32ull * (min(pr + 2, pLimit) + 1)));
     };
 
     u32 w0 = 0, w1 = 0, w2 = 0, r = 0;               // raw stream words: the window starts at bit r of w0 and spans w0..w2
     u32 ctr = 0;                                      // ring read cursor: (ctr >> 29) = slot of the next word to fetch
-    u32 q = 0;                                        // chunk held in P (chunks 0..q-1 are consumed or in the ring)
-    uint4 P = make_uint4(0, 0, 0, 0);
+    u32 q = 0;                                        // next chunk to enter the ring (chunks 0..q-1 are consumed or in it); chunk q -> slots (4q..4q+3) mod 8
+    auto store_next = [&]() {                         // chunk q out of the pending pair; an odd q uses the pair up: fetch the next one
+        u32 const a = ringLane + (q & 1) * (4 * THREADS * 4);
+        bool const lowHalf = (q & 1) != 0;
+        sts_u32(a, lowHalf ? m3 : m7); sts_u32(a + THREADS * 4, lowHalf ? m2 : m6);
+        sts_u32(a + 2 * THREADS * 4, lowHalf ? m1 : m5); sts_u32(a + 3 * THREADS * 4, lowHalf ? m0 : m4);
+        q++;
+        if (!(q & 1)) load_pair(q >> 1);
+    };
     // Words written but not yet fetched: U = 4q - (absolute index of the next word to fetch).  The ring is topped up at two
-    // kinds of check, 8 symbols (at most 3 fetched words) apart: the group-start check stores the pending chunk when U <= 4, the
+    // kinds of check, 8 symbols (at most 3 fetched words) apart: the group-start check stores the next chunk when U <= 4, the
     // mid-group check only when U <= 3.  Induction: U >= 5 after a group-start check, hence >= 2 at the mid-group one and
     // >= 4 after it, hence >= 1 at the next group start -- U stays in [1, 8] at every check, so it is recoverable from the
     // slot numbers alone, and the ring never runs dry whatever the code lengths.  On typical data only the group-start
-    // check stores: the 16-byte load it issues has 16 symbols of work to land before the next store of this WARP touches
-    // the same registers (the scoreboard is per warp, not per lane: a store every 8 symbols exposed the DRAM latency).
+    // check stores, so a load has 16 symbols of work to land before the next store of this WARP touches its registers (the
+    // scoreboard is per warp, not per lane: a store every 8 symbols exposed the latency).
     auto unread = [&]() -> u32 { return ((4 * q - (ctr >> 29) - 1) & 7) + 1; };
-    // The load of chunk q is consumed 16 symbols later -- not enough to cover a DRAM round trip under load (ncu: the store of P
-    // waited on it for 16% of all samples) -- so every top-up also asks the L2 for the sector four chunks further down the
-    // stream; by the time the demand load is issued it is an L2 hit, which 16 symbols of decoding do cover.
-    auto top_up = [&](u32 threshold) {
-        if (unread() <= threshold) {
-            store_chunk(q, P);
-            q++;
-            P = load_chunk(q);
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(chunkTop - 16ull * (min(q + 4, qLimit) + 1)));
-        }
+    auto top_up = [&](u32 threshold) { if (unread() <= threshold) store_next(); };
+    auto fetch_word = [&]() -> u32 {
+        u32 const v = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4));
+        ctr += 1u << 29;
+        return v;
     };
 
-    if (go) {                                         // chunks 0 and 1 fill the ring, the window words come out of it, chunk 2 follows
-        store_chunk(0, load_chunk(0)); store_chunk(1, load_chunk(1));
-        q = 2; P = load_chunk(2);
+    if (go) {                                         // the first pair fills the ring, the window words come out of it
+        u32 const k0 = c0 >> 5;                       // first word of the window: 0..8
         r = c0 & 31;
-        ctr = (c0 >> 5) << 29;                        // first word of the window: 0..4
-        w0 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); ctr += 1u << 29;
-        w1 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); ctr += 1u << 29;
-        w2 = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4)); ctr += 1u << 29;
-        top_up(4);                                    // 1..5 words unread: bring the ring to >= 5
+        q = 2 * (k0 >> 3);
+        load_pair(q >> 1);
+        store_next(); store_next();                   // ring full: words 4q-8 .. 4q-1; the next pair is on its way
+        ctr = (k0 & 7) << 29;
+        w0 = fetch_word(); if (!(ctr >> 29)) store_next();      // wrapped to slot 0 = everything fetched: the next chunk goes there
+        w1 = fetch_word(); if (!(ctr >> 29)) store_next();
+        w2 = fetch_word(); if (!(ctr >> 29)) store_next();
+        top_up(4);                                    // bring the ring to >= 5 unread words
     }
 
     // ---- decode ----
