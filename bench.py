@@ -423,14 +423,16 @@ def run_b200(a):
         # transfer of the widest block, rounded to 64 B; +16 B on the way in because the kernels read aligned 16-byte pieces)
         cs_np = h_cs.numpy()
         wid_out = wid_in = 0
-        for c0 in range(0, nb, 2048):
-            mx = int(cs_np[c0:c0 + 2048].max()); cbk = min(2048, nb - c0)
+        hchunk = int(os.environ.get("FSEB200_HOST_CHUNK_BLOCKS", "2048"))           # capi.cu chunk_blocks()
+        for c0 in range(0, nb, hchunk):
+            mx = int(cs_np[c0:c0 + hchunk].max()); cbk = min(hchunk, nb - c0)
             wid_out += min(SLOT, (mx + 63) & ~63) * cbk
             wid_in += min(SLOT, (mx + 16 + 63) & ~63) * cbk
         e2e = {"value": round(world * n * ke / wall / 1e9, 3), "unit": "GB/s", "steps": ke, "roundtrip_ok": ok_e2e,
                "h2d_bytes_per_step": n + wid_in + 8 * nb, "d2h_bytes_per_step": wid_out + 8 * nb + n + 8 * nb,
-               "api": "FSEB200_compress_host + FSEB200_decompress_host (pinned host buffers, 64 MiB chunks on 3 streams)",
-               "note": "PCIe-bound: each call moves 1 GiB one way (about 19.5 ms at the measured 55 GB/s)"}
+               "api": "FSEB200_compress_host + FSEB200_decompress_host (pinned host buffers, %d-block chunks on 4 streams)" % hchunk,
+               "note": "PCIe-bound: each of the two calls moves the uncompressed GiB one way (19.3 ms at the measured 55.6 GB/s) while the "
+                       "compressed side goes the other way; both one-way bounds together cap this metric at about 28 GB/s per GPU"}
         del h_src, h_c, h_out
 
     # ---- BASELINE configs[3] shape, reported separately: the root scatters the compressed shards over NVLink, every

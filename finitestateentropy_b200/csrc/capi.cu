@@ -742,11 +742,11 @@ FSEB_API size_t FSEB200_genU16(void* dDst, size_t nSymbols, size_t streamOffset,
 // ================================================================================================
 namespace {
 struct HostPipe {
-    enum { NS = 3 };
-    cudaStream_t st[NS] = { nullptr, nullptr, nullptr };
-    unsigned char* dA[NS] = { nullptr, nullptr, nullptr };   // uncompressed side
-    unsigned char* dB[NS] = { nullptr, nullptr, nullptr };   // compressed slots
-    u64* dS[NS] = { nullptr, nullptr, nullptr };             // sizes + results
+    enum { NS = 4 };
+    cudaStream_t st[NS] = {};
+    unsigned char* dA[NS] = {};   // uncompressed side
+    unsigned char* dB[NS] = {};   // compressed slots
+    u64* dS[NS] = {};             // sizes + results
     size_t capA = 0, capB = 0, capS = 0;
     std::mutex mu;
     void ensure(size_t a, size_t b, size_t s)
@@ -758,7 +758,15 @@ struct HostPipe {
     }
 };
 HostPipe& pipe() { static HostPipe p[MAX_DEVICES]; return p[current_device()]; }
-const size_t CHUNK_BLOCKS = 2048;                                     // 64 MiB of 32 KB blocks per chunk
+// Blocks per pipeline chunk (FSEB200_HOST_CHUNK_BLOCKS, default 2048 = 64 MiB of 32 KB blocks).  Measured on a B200 (1 GiB P14,
+// four streams): 2048 -> compress 21.1 ms / decompress 21.9 ms; 512 -> 21.2 / 23.9; 256 -> 21.7 / 25.0 (smaller chunks shorten
+// the pipeline's fill and drain but leave the decode kernel a fraction of a wave per launch).  One-way PCIe bound: 19.3 ms.
+size_t chunk_blocks()
+{
+    static size_t const v = [] { const char* e = std::getenv("FSEB200_HOST_CHUNK_BLOCKS"); long n = e ? std::atol(e) : 2048; return (size_t)(n < 64 ? 64 : n > 65536 ? 65536 : n); }();
+    return v;
+}
+#define CHUNK_BLOCKS chunk_blocks()
 }
 
 FSEB_API size_t FSEB200_compress_host(int codec, void* hCBuf, size_t slot, size_t* hCSizes, const void* hSrc, size_t srcTotal,
