@@ -226,6 +226,35 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(inside), "samples_total": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and, by first touch, the pinned host buffers it allocates next) to the NUMA node its GPU hangs off: on the
+    8-GPU box GPUs 0-3 sit on node 0 and 4-7 on node 1, and a rank whose host buffers live on the other socket pays the
+    inter-socket link on every PCIe transfer (round 1: e2e scaling efficiency 0.535 at N=8).  Best effort; returns what it did."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "single-node host"}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        try:                                                       # memory policy: prefer the node (set_mempolicy, x86-64 syscall 238)
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(1 << node)
+            libc.syscall(238, 1, C.byref(mask), C.c_ulong(64))     # MPOL_PREFERRED
+        except Exception:
+            pass
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as exc:
+        return {"numa_node": None, "note": repr(exc)[:80]}
+
+
 def measured_peak():
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -395,6 +424,8 @@ def run_b200(a):
     # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside the timed region) ----
     e2e = None
     if not a.no_e2e:
+        aff0 = os.sched_getaffinity(0)
+        numa = bind_to_gpu_numa_node(local)
         h_src = torch.empty(n, dtype=torch.uint8, pin_memory=True); h_src.copy_(src)
         h_c = torch.empty(nb * SLOT + 64, dtype=torch.uint8, pin_memory=True)
         h_cs = torch.empty(nb, dtype=torch.int64, pin_memory=True)
@@ -430,25 +461,78 @@ def run_b200(a):
             wid_in += min(SLOT, (mx + 16 + 63) & ~63) * cbk
         e2e = {"value": round(world * n * ke / wall / 1e9, 3), "unit": "GB/s", "steps": ke, "roundtrip_ok": ok_e2e,
                "h2d_bytes_per_step": n + wid_in + 8 * nb, "d2h_bytes_per_step": wid_out + 8 * nb + n + 8 * nb,
+               "host_binding": numa,
                "api": "FSEB200_compress_host + FSEB200_decompress_host (pinned host buffers, %d-block chunks on 4 streams)" % hchunk,
                "note": "PCIe-bound: each of the two calls moves the uncompressed GiB one way (19.3 ms at the measured 55.6 GB/s) while the "
                        "compressed side goes the other way; both one-way bounds together cap this metric at about 28 GB/s per GPU"}
         del h_src, h_c, h_out
+        try:                                                       # the CPU baseline below must see every core again
+            os.sched_setaffinity(0, aff0)
+            C.CDLL(None).syscall(238, 0, None, C.c_ulong(0))       # MPOL_DEFAULT
+        except Exception:
+            pass
 
     # ---- BASELINE configs[3] shape, reported separately: the root scatters the compressed shards over NVLink, every
-    #      rank decodes its shard, the root gathers the decoded shards.  Bounded by the root's link, not by the codec. ----
+    #      rank decodes its shard, the root gathers the decoded shards.  Bounded by the root's NVLink port, not by the codec:
+    #      (N-1) GiB must come back through it (about 770 GB/s measured per direction).  So the work is cut to fit the link:
+    #        * only USED bytes travel: each shard is re-pitched on the root from 33,548-byte slots to rows of the widest block
+    #          (+ slack for the decoder's 32-byte reads); the decoder takes any slot stride, so nobody unpacks anything;
+    #        * the shard is cut into K pieces, and scatter (root egress) and gather (root ingress) use two NCCL communicators,
+    #          i.e. two streams: piece k+1 goes out while piece k is decoded and piece k-1 comes back. ----
     sg = None
     if dist is not None and world > 1 and not a.no_sg and a.codec == "huf":
-        parts_c = [torch.empty_like(cbuf) for _ in range(world)] if rank == 0 else None
-        parts_s = [torch.empty_like(cs) for _ in range(world)] if rank == 0 else None
-        dist.gather(cbuf, parts_c, dst=0); dist.gather(cs, parts_s, dst=0)           # setup: the root now holds every shard, compressed
-        parts_o = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
-        rc = torch.empty_like(cbuf); rs = torch.empty_like(cs)
+        K = 8 if nb % 8 == 0 else 1
+        nbk = nb // K                                               # blocks per piece
+        wmax = cs.max().reshape(1).clone()
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)                 # one pitch for every shard
+        W = (int(wmax.item()) + 32 + 63) // 64 * 64                 # widest block + the decoder's 32-byte read-ahead, 64-byte multiple
+        W = min(W, SLOT)
+        pg_s = dist.new_group(list(range(world))); pg_g = dist.new_group(list(range(world)))
+        packed = cbuf[:nb * SLOT].view(nb, SLOT)[:, :W].contiguous()                    # [nb, W] (setup, on every rank)
+        pad = torch.zeros(64, dtype=torch.uint8, device=dev)
+        root_c = root_s = parts_o = None
+        if rank == 0:
+            root_c = [torch.empty(nb * W + 64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            root_s = [torch.empty_like(cs) for _ in range(world)]
+            parts_o = [torch.empty_like(out) for _ in range(world)]
+        mine_c = torch.cat([packed.view(-1), pad])
+        dist.gather(mine_c, root_c, dst=0); dist.gather(cs, root_s, dst=0)             # setup: the root now holds every shard, packed
+        rc = torch.empty(nb * W + 64, dtype=torch.uint8, device=dev); rs = torch.empty_like(cs)
+        cur = torch.cuda.current_stream()
+
+        def piece_c(t, k):
+            return t[k * nbk * W: (k + 1) * nbk * W + (64 if k == K - 1 else 0)]
 
         def sg_step():
-            dist.scatter(rc, parts_c, src=0); dist.scatter(rs, parts_s, src=0)
-            dec(rc, rs, n, BLOCK, SLOT, out=out, results=res, orig=None)
-            dist.gather(out, parts_o, dst=0)
+            if rank == 0:
+                works = []
+                for k in range(K):                                   # egress: piece k of every shard, one NCCL group per piece
+                    ops = [dist.P2POp(dist.isend, piece_c(root_c[r], k), r, pg_s) for r in range(1, world)]
+                    ops += [dist.P2POp(dist.isend, root_s[r][k * nbk:(k + 1) * nbk], r, pg_s) for r in range(1, world)]
+                    works += dist.batch_isend_irecv(ops)
+                for k in range(K):                                   # ingress: decoded piece k of every shard
+                    ops = [dist.P2POp(dist.irecv, parts_o[r][k * nbk * BLOCK:(k + 1) * nbk * BLOCK], r, pg_g) for r in range(1, world)]
+                    works += dist.batch_isend_irecv(ops)
+                for k in range(K):                                   # the root's own shard, piece by piece like everybody else
+                    dec(piece_c(root_c[0], k), root_s[0][k * nbk:(k + 1) * nbk], nbk * BLOCK, BLOCK, W,
+                        out=parts_o[0][k * nbk * BLOCK:(k + 1) * nbk * BLOCK], results=res[k * nbk:(k + 1) * nbk], orig=None)
+                for w in works:
+                    w.wait()
+            else:
+                recvs = []
+                for k in range(K):
+                    recvs.append(dist.batch_isend_irecv([dist.P2POp(dist.irecv, piece_c(rc, k), 0, pg_s),
+                                                         dist.P2POp(dist.irecv, rs[k * nbk:(k + 1) * nbk], 0, pg_s)]))
+                sends = []
+                for k in range(K):
+                    for w in recvs[k]:
+                        w.wait()                                     # the compute stream waits for piece k (no host block)
+                    dec(piece_c(rc, k), rs[k * nbk:(k + 1) * nbk], nbk * BLOCK, BLOCK, W,
+                        out=out[k * nbk * BLOCK:(k + 1) * nbk * BLOCK], results=res[k * nbk:(k + 1) * nbk], orig=None)
+                    sends += dist.batch_isend_irecv([dist.P2POp(dist.isend, out[k * nbk * BLOCK:(k + 1) * nbk * BLOCK], 0, pg_g)])
+                for w in sends:
+                    w.wait()
+        out.zero_()
         sg_step()
         barrier()
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
@@ -460,16 +544,24 @@ def run_b200(a):
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        okt = torch.tensor([1 if torch.equal(out, src) else 0], dtype=torch.int32, device=dev)
-        if rank == 0:
-            okt &= int(torch.equal(parts_o[0], src))
+        okt = torch.tensor([1 if torch.equal(out if rank else parts_o[0], src) else 0], dtype=torch.int32, device=dev)
+        if rank == 0:                                               # every gathered shard is the generator's stream for that rank
+            chk = torch.empty_like(src)
+            for r in range(1, world):
+                assert wl.gen_device(L, chk.data_ptr(), n, r * n, stream) == 0
+                okt &= int(torch.equal(parts_o[r], chk))
+            del chk
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         ok_sg = bool(int(okt.cpu()[0]))
         ms = float(tg.cpu()[0]) / ks
-        sg = {"what": "root scatters compressed Huff0 shards (full slots), all ranks decode, root gathers decoded shards; NCCL send/recv over NVLink",
+        link = 770.0                                                # GB/s per direction per GPU, measured (B200_PROFILING.md)
+        bound_ms = max((world - 1) * n, (world - 1) * nb * W) / link / 1e6
+        sg = {"what": "BASELINE configs[3]: root scatters compressed Huff0 shards (rows re-pitched to the widest block, %d pieces), all ranks "
+                      "decode, root gathers decoded shards; scatter and gather on separate NCCL communicators so egress / decode / ingress overlap" % K,
               "decode_gbs_incl_transfers": round(world * n / (ms * 1e-3) / 1e9, 2), "ms_per_step": round(ms, 3), "steps": ks,
-              "bytes_scattered": (world - 1) * int(cbuf.numel()), "bytes_gathered": (world - 1) * n, "roundtrip_ok": ok_sg}
-        del parts_c, parts_o, rc
+              "bytes_scattered": (world - 1) * nb * W, "bytes_gathered": (world - 1) * n, "row_pitch": W, "pieces": K,
+              "root_link_bound_ms": round(bound_ms, 3), "frac_of_link_bound": round(bound_ms / ms, 3), "roundtrip_ok": ok_sg}
+        del root_c, parts_o, rc, packed, mine_c
 
     if rank != 0:
         if dist is not None:
