@@ -50,7 +50,8 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr u32 MIN_ROWS = 160;     // a hard block parks its canonical-code arrays in 156 rows of its own column
 constexpr u32 PARK_RANKEND = 128, PARK_LISTSTART = 142;
 
-struct __align__(16) Facts {      // per-CTA facts about its 64 block columns (1 KB)
+struct __align__(16) Facts {      // per-CTA facts about its 64 block columns (1.25 KB)
+    u32 bid[G];                   // batch index of the block in this column (NOBLOCK = empty column)
     u32 status[G];                // NOERR or (stage<<8 | error code), smallest wins
     u32 hsize[G];                 // tree-header bytes
     u16 dOff[G];                  // D of the row formula
@@ -69,7 +70,8 @@ struct BuildScratch {             // lives in the (not yet used) stream ring whi
     u16 listStart[NWARPS][HUF_MAX_TLOG + 2];   // first position of weight w in the sorted symbol list
 };
 static_assert(sizeof(BuildScratch) <= RING_BYTES, "build scratch must fit in the ring");
-static_assert(sizeof(Facts) == 1024, "Facts layout");
+static_assert(sizeof(Facts) == 1280, "Facts layout");
+constexpr u32 NOBLOCK = 0xFFFFFFFFu;
 
 __host__ __device__ constexpr u32 smem_bytes(u32 rows) { return rows * (G * 2) + RING_BYTES + (u32)sizeof(Facts); }
 
@@ -163,8 +165,12 @@ __device__ void setup_block(u16* tbl, Facts& fx, BuildScratch& bs, u32 rows, int
 
 __global__ void __launch_bounds__(THREADS, 4)
 huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf, const u64* __restrict__ csizes,
-                  u64* __restrict__ results, const u8* __restrict__ orig, u32 flags, u32 gEff, u32 rows)
+                  u64* __restrict__ results, const u8* __restrict__ orig, u32 flags, u32 gEff, u32 rows,
+                  const u32* __restrict__ list, const u32* __restrict__ listCount, u32* __restrict__ deferList, u32* __restrict__ deferCount)
 {
+    // Two passes share this kernel.  Pass A (list == nullptr) walks the batch in order with the four-CTAs-per-SM table budget; a
+    // block whose smallest table does not fit that budget is not decoded but appended to deferList.  Pass B (deferList == nullptr)
+    // walks that list with a larger budget (fewer CTAs per SM); what does not fit even there takes the per-symbol path.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u16* const tbl = reinterpret_cast<u16*>(smem_raw);                                   // [rows][G]
     unsigned char* const ringRaw = smem_raw + rows * (G * 2);
@@ -172,15 +178,17 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     Facts& fx = *reinterpret_cast<Facts*>(ringRaw + RING_BYTES);
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     u32 const blk0 = blockIdx.x * gEff;
-    u32 const blkEnd = min(blk0 + gEff, g.nBlocks);                         // this CTA owns blocks [blk0, blkEnd)
+    u32 const nWork = list ? *listCount : g.nBlocks;
+    if (blk0 >= nWork) return;                                              // pass B is launched for the worst case: most CTAs find nothing
+    u32 const blkEnd = min(blk0 + gEff, nWork);                             // this CTA owns work items [blk0, blkEnd)
 
-    if (tid < G) { fx.status[tid] = NOERR; fx.kind[tid] = 3; fx.hsize[tid] = 0; fx.tlog[tid] = 0; fx.mbits[tid] = 0; fx.cut[tid] = 0; fx.dOff[tid] = 0; fx.hard[tid] = 0; }
+    if (tid < G) { fx.bid[tid] = (blk0 + tid < blkEnd) ? (list ? list[blk0 + tid] : blk0 + tid) : NOBLOCK; fx.status[tid] = NOERR; fx.kind[tid] = 3; fx.hsize[tid] = 0; fx.tlog[tid] = 0; fx.mbits[tid] = 0; fx.cut[tid] = 0; fx.dOff[tid] = 0; fx.hard[tid] = 0; }
     __syncthreads();
 
     // ---- classify blocks and build tables: warp w handles columns w, w+8, ... ----
     for (int j = warp; j < G; j += NWARPS) {
-        u32 const b = blk0 + j;
-        if (b >= blkEnd) continue;                                      // warp-uniform
+        u32 const b = fx.bid[j];
+        if (b == NOBLOCK) continue;                                     // warp-uniform
         u64 const n = block_len(g, b);
         u64 const cs = csizes[b];
         int kind;
@@ -193,15 +201,20 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
         else if (cs == 1) kind = 2;                                                                // :1066
         else kind = 0;
         if (lane == 0) fx.kind[j] = (u8)kind;
-        if (kind == 0) setup_block(tbl, fx, bs, rows, j, cbuf + (u64)b * g.slot, cs, warp);
+        if (kind == 0) {
+            setup_block(tbl, fx, bs, rows, j, cbuf + (u64)b * g.slot, cs, warp);
+            if (deferList && fx.hard[j] && fx.status[j] == NOERR) {     // pass A: hand the block to the pass with the larger table budget
+                if (lane == 0) { deferList[atomicAdd(deferCount, 1u)] = b; fx.kind[j] = 3; }
+            }
+        }
     }
     __syncthreads();                                  // tables and facts complete; the build scratch (ring) is free now
 
     // ---- per-lane stream set-up: thread -> (block column, stream) ----
     int const col = 2 * lane + (warp >> 2);          // a warp sees the 32 even (or odd) columns = 32 distinct banks
     int const strm = warp & 3;
-    u32 const b = blk0 + col;
-    bool const live = (b < blkEnd) && fx.kind[col] == 0 && fx.status[col] == NOERR;
+    u32 const b = fx.bid[col];
+    bool const live = (b != NOBLOCK) && fx.kind[col] == 0 && fx.status[col] == NOERR;
     u32 const n = live ? block_len(g, b) : 0;
     u32 const seg = (n + 3) / 4;
     u32 segLen = 0;                                  // symbols this lane must produce
@@ -400,8 +413,8 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     }
     __syncthreads();
     if (tid < G) {
-        u32 const bb = blk0 + tid;
-        if (bb < blkEnd && fx.kind[tid] == 0) {
+        u32 const bb = fx.bid[tid];
+        if (bb != NOBLOCK && fx.kind[tid] == 0) {
             u32 const st = fx.status[tid];
             u64 rv = (st == NOERR) ? (u64)block_len(g, bb) : err(st & 0xFF);
             // Rejected only by the exact-consumption rule of the single-symbol decoder: where the reference would have run
@@ -415,7 +428,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     for (int j = 0; j < G; j++) {
         int const kd = fx.kind[j];
         if (kd != 1 && kd != 2) continue;
-        u32 const bb = blk0 + j;
+        u32 const bb = fx.bid[j];
         u32 const nn = block_len(g, bb);
         u64 const cs = csizes[bb];
         u8* const o = dst + (u64)bb * g.blockSize;
@@ -439,33 +452,45 @@ cudaError_t launch_huf_decode(const BatchGeom& g, void* dst, const void* cbuf, c
                               const void* orig, cudaStream_t stream, u32 flags)
 {
     static SmemOptIn optin;
-    static u32 rowsCfg = 0;
-    if (!rowsCfg) {                                                    // FSEB200_HUFD_ROWS: table rows per CTA (372 -> 55.75 KB: four CTAs per SM)
-        const char* const e = std::getenv("FSEB200_HUFD_ROWS");
-        u32 v = e ? (u32)std::atoi(e) : 372u;
-        if (v < hufd::MIN_ROWS) v = hufd::MIN_ROWS;
-        if (v > 1704) v = 1704;
-        rowsCfg = v;
-    }
-    u32 const rows = rowsCfg;
-    size_t const smem = hufd::smem_bytes(rows);
-    int const dev = current_device();
-    cudaError_t const e = optin.ensure(hufd::huf_decode_kernel, dev, (int)smem);
-    if (e != cudaSuccess) return e;
+    // Table rows per CTA.  Pass A: 370 rows -> 55.75 KB -> FOUR CTAs (256 blocks) per SM; pass B, for the blocks whose tables
+    // need more (wide, flat alphabets: probagen P <= 10%): 808 rows -> two CTAs per SM.  FSEB200_HUFD_ROWS / _ROWS_B override.
+    static u32 const rowsA = [] { const char* e = std::getenv("FSEB200_HUFD_ROWS"); u32 v = e ? (u32)std::atoi(e) : 370u; return v < hufd::MIN_ROWS ? hufd::MIN_ROWS : v > 1700u ? 1700u : v; }();
+    static u32 const rowsB = [] { const char* e = std::getenv("FSEB200_HUFD_ROWS_B"); u32 v = e ? (u32)std::atoi(e) : 808u; return v > 1700u ? 1700u : v; }();   // 0 = single pass
     if (g.nBlocks == 0) return cudaSuccess;
-    // Every lane decodes a whole stream, so a CTA's run time hardly depends on how many blocks it holds: give each
+    int const dev = current_device();
+    size_t const smemA = hufd::smem_bytes(rowsA);
+    cudaError_t e = optin.ensure(hufd::huf_decode_kernel, dev, (int)(rowsB > rowsA ? hufd::smem_bytes(rowsB) : smemA));
+    if (e != cudaSuccess) return e;
+    bool const twoPass = rowsB > rowsA;
+    u32* scratch = nullptr;
+    if (twoPass) {
+        scratch = (u32*)stream_scratch(1, stream, ((size_t)g.nBlocks + 1) * sizeof(u32), &e);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(scratch, 0, sizeof(u32), stream);              // [0] = number of deferred blocks, [1..] = their indices
+        if (e != cudaSuccess) return e;
+    }
+    // Pass A.  Every lane decodes a whole stream, so a CTA's run time hardly depends on how many blocks it holds: give each
     // SM the same number of blocks per round (a round = the CTAs resident at once).
     int perSm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, hufd::huf_decode_kernel, hufd::THREADS, smem) != cudaSuccess || perSm < 1) perSm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, hufd::huf_decode_kernel, hufd::THREADS, smemA) != cudaSuccess || perSm < 1) perSm = 1;
     u32 const slots = (u32)perSm * (u32)device_sm_count(dev);
     u32 const rounds = (g.nBlocks + slots * hufd::G - 1) / (slots * hufd::G);
     u32 gEff = (g.nBlocks + slots * rounds - 1) / (slots * rounds);
     if (gEff > (u32)hufd::G) gEff = hufd::G;
     if (gEff < 1) gEff = 1;
     unsigned const grid = (g.nBlocks + gEff - 1) / gEff;
-    hufd::huf_decode_kernel<<<grid, hufd::THREADS, smem, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig, flags, gEff, rows);
-    cudaError_t const e2 = cudaGetLastError();
-    if (e2 != cudaSuccess || flags == 1u) return e2;                    // X1-only semantics: no second pass
+    hufd::huf_decode_kernel<<<grid, hufd::THREADS, smemA, stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig, flags, gEff, rowsA,
+                                                                    nullptr, nullptr, twoPass ? scratch + 1 : nullptr, scratch);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (twoPass) {   // pass B over the deferred list; its length lives on the device, so the grid covers the worst case and idle CTAs leave at once
+        unsigned const gridB = (g.nBlocks + hufd::G - 1) / hufd::G;
+        hufd::huf_decode_kernel<<<gridB, hufd::THREADS, hufd::smem_bytes(rowsB), stream>>>(g, (u8*)dst, (const u8*)cbuf, csizes, results, (const u8*)orig, flags,
+                                                                                            (u32)hufd::G, rowsB, scratch + 1, scratch, nullptr, nullptr);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (flags == 1u) return cudaSuccess;                                // X1-only semantics: no verdict pass
     return launch_huf_x2_fixup(g, dst, cbuf, csizes, results, stream);
 }
 

@@ -46,4 +46,30 @@ struct SmemOptIn {
     }
 };
 
+// Grow-only device scratch, one buffer per (purpose, device, stream): successive calls on a stream reuse it (stream order makes
+// that safe), a different stream gets its own.  Returns nullptr and sets *err on failure.
+inline void* stream_scratch(int purpose, cudaStream_t stream, size_t bytes, cudaError_t* err)
+{
+    struct Slot { int purpose, dev; cudaStream_t s; void* p; size_t cap; };
+    static std::mutex mu;
+    static Slot slots[256];
+    static int nSlots = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    int const dev = current_device();
+    Slot* hit = nullptr;
+    for (int i = 0; i < nSlots; i++) if (slots[i].purpose == purpose && slots[i].s == stream && slots[i].dev == dev) { hit = &slots[i]; break; }
+    if (!hit) {
+        if (nSlots == 256) { *err = cudaErrorMemoryAllocation; return nullptr; }
+        slots[nSlots] = Slot{ purpose, dev, stream, nullptr, 0 }; hit = &slots[nSlots++];
+    }
+    *err = cudaSuccess;
+    if (hit->cap < bytes) {
+        if (hit->p) { cudaStreamSynchronize(stream); cudaFree(hit->p); hit->p = nullptr; hit->cap = 0; }
+        *err = cudaMalloc(&hit->p, bytes);
+        if (*err != cudaSuccess) return nullptr;
+        hit->cap = bytes;
+    }
+    return hit->p;
+}
+
 }  // namespace fseb
