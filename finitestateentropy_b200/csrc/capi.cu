@@ -11,6 +11,7 @@
 // aborts loudly.  Only scalar helpers (bounds, error names, table-log arithmetic) run on the host.
 #include "common.cuh"
 #include "micro.h"
+#include "fse_b200.h"
 #include "launch_util.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +21,7 @@
 namespace fseb {
 cudaError_t launch_huf_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t, u32 flags);
 cudaError_t launch_huf_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
+cudaError_t launch_huf_encode_using_ctable(const BatchGeom&, void*, u64*, const void*, const u32*, cudaStream_t);
 cudaError_t launch_fse_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t);
 cudaError_t launch_fse_encode(const BatchGeom&, void*, u64*, const void*, unsigned, unsigned, cudaStream_t);
 cudaError_t launch_fseu16_decode(const BatchGeom&, void*, const void*, const u64*, u64*, const void*, cudaStream_t);
@@ -175,6 +177,18 @@ FSEB_DECL_DEC(FSEB200_FSE_decompress_batch, launch_fse_decode, (1u << 30))
 FSEB_DECL_ENC(FSEB200_FSE_compress_batch, launch_fse_encode, (1u << 30))
 FSEB_DECL_DEC(FSEB200_FSEU16_decompress_batch, launch_fseu16_decode, (1u << 30))
 FSEB_DECL_ENC(FSEB200_FSEU16_compress_batch, launch_fseu16_encode, (1u << 30))
+
+// Table reuse across blocks: the whole batch coded with ONE caller-supplied HUF_CElt table (256 cells on the device,
+// the layout HUF_buildCTable produces: val | nbBits << 16).  dCSizes[b] is what HUF_compress4X_usingCTable (lib/huf.h:191,
+// huf_compress.c:552-610) returns for block b with that table: 6 + the four stream sizes, or 0 (block shorter than 12 bytes, or a
+// stream does not fit its slot).  No histogram, no tree, no header: the shape programs/bench.c:610-633 times for FSE and
+// HUF_compress4X_repeat (huf_compress.c:664-712) reduces to when the previous table is kept.
+FSEB_API size_t FSEB200_HUF_compress4X_usingCTable_batch(void* dCBuf, size_t slot, size_t* dCSizes, const void* dSrc, size_t srcTotal, size_t blockSize,
+                                                         const unsigned* dCTable, void* stream)
+{
+    if (blockSize == 0 || blockSize > HUF_BLOCK_MAX || slot > 0xFFFFFFFFull || !dCTable) return (size_t)err(E_SRC_WRONG);
+    return ok_or_generic(launch_huf_encode_using_ctable(geom(srcTotal, blockSize, slot), dCBuf, (u64*)dCSizes, dSrc, dCTable, (cudaStream_t)stream));
+}
 
 FSEB_API size_t FSEB200_batch_blocks(size_t total, size_t blockSize) { return blockSize ? (total + blockSize - 1) / blockSize : 0; }
 FSEB_API int FSEB200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
@@ -648,6 +662,100 @@ FSEB_API size_t HUF_compress1X(void* dst, size_t dstSize, const void* src, size_
     if (hSize + cSize >= srcSize - 1) return 0;                                      // :625
     return hSize + cSize;
 }
+// ---- table reuse, one block per call (lib/huf.h:194-208,291-300): HUF_compress_internal's repeat logic (huf_compress.c:637-724) composed
+//      from the table-level calls, every data step on the GPU.  `repeat` is HUF_repeat {none 0, check 1, valid 2}. ----
+namespace {
+size_t huf_compress_ctable_internal(bool four, unsigned char* ostart, unsigned char* op, unsigned char* oend, const void* src, size_t srcSize, const unsigned* CTable)
+{
+    size_t const cSize = four ? HUF_compress4X_usingCTable(op, (size_t)(oend - op), src, srcSize, CTable)      // huf_compress.c:612-627
+                              : HUF_compress1X_usingCTable(op, (size_t)(oend - op), src, srcSize, CTable);
+    if (is_err(cSize)) return cSize;
+    if (cSize == 0) return 0;
+    op += cSize;
+    if ((size_t)(op - ostart) >= srcSize - 1) return 0;
+    return (size_t)(op - ostart);
+}
+size_t huf_compress_repeat(bool four, void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned huffLog,
+                           void* workSpace, size_t wkspSize, unsigned* oldHufTable, int* repeat, int preferRepeat)
+{
+    unsigned char* const ostart = (unsigned char*)dst; unsigned char* const oend = ostart + dstSize; unsigned char* op = ostart;
+    if (((size_t)workSpace & 3) != 0) return (size_t)err(E_GENERIC);                 // :652-653
+    if (wkspSize < (6 << 10)) return (size_t)err(E_WKSP_TOO_SMALL);
+    if (!srcSize || !dstSize) return 0;
+    if (srcSize > HUF_BLOCK_MAX) return (size_t)err(E_SRC_WRONG);
+    if (huffLog > HUF_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (maxSymbolValue > HUF_MAX_SV) return (size_t)err(E_MSV_TOO_LARGE);
+    if (!maxSymbolValue) maxSymbolValue = HUF_MAX_SV;
+    if (!huffLog) huffLog = HUF_DEF_TLOG;
+    if (preferRepeat && repeat && *repeat == 2) return huf_compress_ctable_internal(four, ostart, op, oend, src, srcSize, oldHufTable);   // :665-669
+    unsigned count[256]; unsigned ctable[256];
+    size_t const largest = HIST_count(count, &maxSymbolValue, src, srcSize);
+    if (is_err(largest)) return largest;
+    if (largest == srcSize) { ostart[0] = ((const unsigned char*)src)[0]; return 1; }
+    if (largest <= (srcSize >> 7) + 4) return 0;
+    for (unsigned s2 = maxSymbolValue + 1; s2 < 256; s2++) count[s2] = 0;
+    if (repeat && *repeat == 1 && !HUF_validateCTable(oldHufTable, count, maxSymbolValue)) *repeat = 0;                              // :679-683
+    if (preferRepeat && repeat && *repeat != 0) return huf_compress_ctable_internal(four, ostart, op, oend, src, srcSize, oldHufTable);
+    huffLog = HUF_optimalTableLog(huffLog, srcSize, maxSymbolValue);
+    size_t const maxBits = HUF_buildCTable(ctable, count, maxSymbolValue, huffLog);
+    if (is_err(maxBits)) return maxBits;
+    huffLog = (unsigned)maxBits;
+    for (unsigned s2 = maxSymbolValue + 1; s2 < 256; s2++) ctable[s2] = 0;                                                          // :699-701
+    size_t const hSize = HUF_writeCTable(op, dstSize, ctable, maxSymbolValue, huffLog);
+    if (is_err(hSize)) return hSize;
+    if (repeat && *repeat != 0) {                                                                                                   // :706-713
+        size_t const oldSize = HUF_estimateCompressedSize(oldHufTable, count, maxSymbolValue);
+        size_t const newSize = HUF_estimateCompressedSize(ctable, count, maxSymbolValue);
+        if (oldSize <= hSize + newSize || hSize + 12 >= srcSize) return huf_compress_ctable_internal(four, ostart, op, oend, src, srcSize, oldHufTable);
+    }
+    if (hSize + 12ul >= srcSize) return 0;
+    op += hSize;
+    if (repeat) *repeat = 0;
+    if (oldHufTable) std::memcpy(oldHufTable, ctable, sizeof(ctable));
+    return huf_compress_ctable_internal(four, ostart, op, oend, src, srcSize, ctable);
+}
+}
+FSEB_API size_t HUF_compress4X_repeat(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned tableLog,
+                                      void* workSpace, size_t wkspSize, unsigned* hufTable, int* repeat, int preferRepeat, int bmi2)   // lib/huf.h:204
+{ (void)bmi2; return huf_compress_repeat(true, dst, dstSize, src, srcSize, maxSymbolValue, tableLog, workSpace, wkspSize, hufTable, repeat, preferRepeat); }
+FSEB_API size_t HUF_compress1X_repeat(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned tableLog,
+                                      void* workSpace, size_t wkspSize, unsigned* hufTable, int* repeat, int preferRepeat, int bmi2)   // lib/huf.h:296
+{ (void)bmi2; return huf_compress_repeat(false, dst, dstSize, src, srcSize, maxSymbolValue, tableLog, workSpace, wkspSize, hufTable, repeat, preferRepeat); }
+
+// HUF_readCTable (lib/huf.h:231, huf_compress.c:149-198): the header is parsed on the GPU (HUF_readStats); what remains is the
+// O(alphabet) canonical numbering of the codes, host arithmetic like the other table helpers.
+FSEB_API size_t HUF_readCTable(unsigned* CTable, unsigned* maxSymbolValuePtr, const void* src, size_t srcSize, unsigned* hasZeroWeights)
+{
+    unsigned char w[256]; unsigned rank[17]; unsigned nbSym = 0, tl = 0;
+    size_t const readSize = HUF_readStats(w, 256, rank, &nbSym, &tl, src, srcSize);
+    if (is_err(readSize)) return readSize;
+    if (tl > HUF_MAX_TLOG) return (size_t)err(E_TLOG_TOO_LARGE);
+    if (nbSym > *maxSymbolValuePtr + 1) return (size_t)err(E_MSV_TOO_SMALL);
+    unsigned nbBits[256]; unsigned short perRank[HUF_MAX_TLOG + 2] = { 0 }, valPerRank[HUF_MAX_TLOG + 2] = { 0 };
+    *hasZeroWeights = 0;
+    for (unsigned n = 0; n < nbSym; n++) { *hasZeroWeights |= (w[n] == 0); nbBits[n] = w[n] ? (tl + 1 - w[n]) & 0xFF : 0; perRank[nbBits[n]]++; }
+    {   unsigned short mn = 0;
+        for (unsigned n = tl; n > 0; n--) { valPerRank[n] = mn; mn = (unsigned short)(mn + perRank[n]); mn >>= 1; }
+    }
+    for (unsigned n = 0; n < nbSym; n++) CTable[n] = (unsigned)(valPerRank[nbBits[n]]++) | (nbBits[n] << 16);
+    *maxSymbolValuePtr = nbSym - 1;
+    return readSize;
+}
+
+FSEB_API size_t HUF_decompress1X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize)                                          // lib/huf.h:304
+{
+    static thread_local unsigned DTable[1 + 4096];
+    DTable[0] = 12u * 0x01000001u;                                                  // HUF_CREATE_STATIC_DTABLEX2(DTable, HUF_TABLELOG_MAX)
+    size_t const hSize = HUF_readDTableX2(DTable, cSrc, cSrcSize);
+    if (is_err(hSize)) return hSize;
+    if (hSize >= cSrcSize) return (size_t)err(E_SRC_WRONG);                         // huf_decompress.c:882
+    return HUF_decompress1X2_usingDTable(dst, dstSize, (const unsigned char*)cSrc + hSize, cSrcSize - hSize, DTable);
+}
+FSEB_API size_t HUF_decompress1X_usingDTable_bmi2(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable, int bmi2)   // lib/huf.h:329
+{ (void)bmi2; return HUF_decompress1X_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable); }
+FSEB_API size_t HUF_decompress4X_usingDTable_bmi2(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable, int bmi2)   // lib/huf.h:333
+{ (void)bmi2; return HUF_decompress4X_usingDTable(dst, maxDstSize, cSrc, cSrcSize, DTable); }
+
 FSEB_API size_t HUF_decompress1X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable)  // lib/huf.h:320
 {
     unsigned const type = (DTable[0] >> 8) & 0xFF, tl = (DTable[0] >> 16) & 0xFF;

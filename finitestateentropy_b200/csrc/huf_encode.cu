@@ -237,7 +237,7 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
 constexpr int THREADS = 128;
 
 __global__ void __launch_bounds__(THREADS)
-huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans)
+huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans, const u32* __restrict__ sharedCT)
 {
     constexpr u32 W = 256;                                          // words of stream window per warp (a group adds <= 88, < 32 wait for the next flush)
     __shared__ uint2 ctab[256];                                     // cells {code, nbBits}: one 8-byte load, no unpacking
@@ -252,7 +252,8 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
     u8* const d = cbuf + (u64)b * g.slot;
     u32 const hSize = P.hSize, total = P.total;
 
-    {   u32 const c0 = P.ctable[tid], c1 = P.ctable[tid + 128];
+    {   const u32* const ct = sharedCT ? sharedCT : P.ctable;       // one caller-supplied table for the whole batch, or the block's own
+        u32 const c0 = ct[tid], c1 = ct[tid + 128];
         ctab[tid] = make_uint2(c0 & 0xFFFFu, c0 >> 16); ctab[tid + 128] = make_uint2(c1 & 0xFFFFu, c1 >> 16);
     }
     for (u32 i = tid; i < 4 * W; i += THREADS) winAll[i] = 0;
@@ -440,7 +441,71 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Table reuse: every block of the batch coded with ONE caller-supplied HUF_CElt table, i.e. per block
+// HUF_compress4X_usingCTable (lib/huf_compress.c:552-610).  No histogram, no tree, no header: the plan kernel disappears and
+// this warp-per-block pass only sums the code lengths of each 4X segment (stream sizes, the writer's capacity rule).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * PLAN_WARPS)
+huf_sizes_kernel(BatchGeom g, u64* __restrict__ csizes, const u8* __restrict__ src, const u32* __restrict__ ct, Plan* __restrict__ plans)
+{
+    __shared__ u8 nbOf[256];
+    unsigned const lane = threadIdx.x & 31u;
+    nbOf[threadIdx.x] = (u8)(ct[threadIdx.x] >> 16);
+    __syncthreads();
+    u32 const b = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
+    if (b >= g.nBlocks) return;
+    u32 const n = block_len(g, b);
+    const u8* const s = src + (u64)b * g.blockSize;
+    u64 const cap = g.slot;
+    Plan& P = plans[b];
+    if (cap < 6 + 1 + 1 + 1 + 8 || n < 12) { if (lane == 0) { P.state = 1; csizes[b] = 0; } return; }   // huf_compress.c:564-565
+    u32 const seg = (n + 3) / 4;
+    u32 bits[4];
+    #pragma unroll 1
+    for (u32 k = 0; k < 4; k++) {
+        u32 const beg = k * seg, end = (k < 3) ? (k + 1) * seg : n;
+        u32 acc = 0;
+        u32 i = beg + lane * 4;
+        if ((reinterpret_cast<u64>(s + beg) & 3) == 0) {
+            for (; i + 4 <= end; i += 128) {
+                u32 const w = __ldg(reinterpret_cast<const u32*>(s + i));
+                acc += nbOf[w & 0xFF] + nbOf[(w >> 8) & 0xFF] + nbOf[(w >> 16) & 0xFF] + nbOf[w >> 24];
+            }
+            for (u32 t = i; t < end && t < i + 4; t++) acc += nbOf[s[t]];      // the lane whose word straddles the end
+        } else for (u32 t = beg + lane; t < end; t += 32) acc += nbOf[s[t]];
+        #pragma unroll
+        for (int dlt = 16; dlt; dlt >>= 1) acc += __shfl_xor_sync(FULL, acc, dlt);
+        bits[k] = acc;
+    }
+    u64 op = 6; bool fits = true;
+    u32 offs[4], lens[4];
+    #pragma unroll
+    for (int t = 0; t < 4; t++) {                                            // :566-600 with bitstream.h:190,246,258
+        u64 const capk = cap - op;
+        u64 const tot = (u64)bits[t] + 1;
+        if (fits && (capk <= 8 || (tot >> 3) >= capk - 8)) fits = false;
+        offs[t] = (u32)op; lens[t] = (u32)((tot + 7) >> 3);
+        op += lens[t];
+    }
+    if (!fits) { if (lane == 0) { P.state = 1; csizes[b] = 0; } return; }
+    if (lane < 4) { P.streamOff[lane] = offs[lane]; P.streamBytes[lane] = lens[lane]; }
+    if (lane == 0) { P.hSize = 0; P.state = 0; P.total = (u32)op; csizes[b] = op; }
+}
+
 }  // namespace hufe
+
+cudaError_t launch_huf_encode_using_ctable(const BatchGeom& g, void* cbuf, u64* csizes, const void* src, const u32* dCTable, cudaStream_t stream)
+{
+    if (g.nBlocks == 0) return cudaSuccess;
+    cudaError_t e;
+    hufe::Plan* const plans = (hufe::Plan*)stream_scratch(2, stream, sizeof(hufe::Plan) * (size_t)g.nBlocks, &e);
+    if (e != cudaSuccess) return e;
+    unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
+    hufe::huf_sizes_kernel<<<grid, 32 * hufe::PLAN_WARPS, 0, stream>>>(g, csizes, (const u8*)src, dCTable, plans);
+    hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, 0, stream>>>(g, (u8*)cbuf, (const u8*)src, plans, dCTable);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const void* src,
                               unsigned msv, unsigned tlog, cudaStream_t stream)
@@ -480,7 +545,7 @@ cudaError_t launch_huf_encode(const BatchGeom& g, void* cbuf, u64* csizes, const
         unsigned const grid = (g.nBlocks + hufe::PLAN_WARPS - 1) / hufe::PLAN_WARPS;
         hufe::huf_plan_kernel<<<grid, 32 * hufe::PLAN_WARPS, smem, stream>>>(g, (u8*)cbuf, csizes, (const u8*)src, msv, tlog, plans, serialHeader);
     }
-    hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, 0, stream>>>(g, (u8*)cbuf, (const u8*)src, plans);
+    hufe::huf_emit_kernel<<<g.nBlocks, hufe::THREADS, 0, stream>>>(g, (u8*)cbuf, (const u8*)src, plans, nullptr);
     e = cudaGetLastError();
     cudaError_t const e2 = asyncScratch ? cudaFreeAsync(plans, stream) : cudaSuccess;
     return e != cudaSuccess ? e : e2;

@@ -56,6 +56,13 @@ size_t FSEB200_FSEU16_decompress_batch(void* dDst, size_t dstTotal, size_t block
                                        const size_t* dCSizes, size_t* dResults, const void* dOrig, void* stream);
 size_t FSEB200_batch_blocks(size_t total, size_t blockSize);
 
+/* Table reuse across blocks (lib/huf.h:191 per block; the shape programs/bench.c:610-633 and HUF_compress4X_repeat,
+ * lib/huf_compress.c:664-712, reduce to when the previous table is kept): every block of the batch is coded with ONE
+ * caller-supplied table -- dCTable = 256 HUF_CElt cells in DEVICE memory, the layout HUF_buildCTable produces.
+ * dCSizes[b] = what HUF_compress4X_usingCTable returns for block b (6 + the four streams, no tree header; 0 if it cannot). */
+size_t FSEB200_HUF_compress4X_usingCTable_batch(void* dCBuf, size_t slot, size_t* dCSizes, const void* dSrc, size_t srcTotal,
+                                                size_t blockSize, const unsigned* dCTable, void* stream);
+
 /* Tier 1b -- the same batches on HOST buffers (pinned or pageable): chunks are copied in, processed and
  * copied out on alternating CUDA streams so that PCIe transfers overlap the kernels.
  * codec: 0 = FSE, 1 = HUF, 2 = FSE-U16.  Synchronous.  Raw / RLE blocks (cSize 0 / 1) are regenerated from
@@ -158,6 +165,16 @@ size_t      HUF_compress1X_usingCTable(void* dst, size_t dstSize, const void* sr
 size_t      HUF_decompress1X1(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
 size_t      HUF_decompress1X_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
 size_t      HUF_decompress1X1_usingDTable(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable);
+/* lib/huf.h:194-208,291-300: table reuse, one block per call.  `repeat` points to a HUF_repeat (an int: none 0, check 1, valid 2) */
+size_t      HUF_compress4X_repeat(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned tableLog,
+                                  void* workSpace, size_t wkspSize, unsigned* hufTable, int* repeat, int preferRepeat, int bmi2);
+size_t      HUF_compress1X_repeat(void* dst, size_t dstSize, const void* src, size_t srcSize, unsigned maxSymbolValue, unsigned tableLog,
+                                  void* workSpace, size_t wkspSize, unsigned* hufTable, int* repeat, int preferRepeat, int bmi2);
+/* lib/huf.h:231,304,329,333 */
+size_t      HUF_readCTable(unsigned* CTable, unsigned* maxSymbolValuePtr, const void* src, size_t srcSize, unsigned* hasZeroWeights);
+size_t      HUF_decompress1X2(void* dst, size_t dstSize, const void* cSrc, size_t cSrcSize);
+size_t      HUF_decompress1X_usingDTable_bmi2(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable, int bmi2);
+size_t      HUF_decompress4X_usingDTable_bmi2(void* dst, size_t maxDstSize, const void* cSrc, size_t cSrcSize, const unsigned* DTable, int bmi2);
 /* lib/fseU16.h:75-79 */
 size_t      FSE_compressU16(void* dst, size_t dstCapacity, const unsigned short* src, size_t srcSize,
                             unsigned maxSymbolValue, unsigned tableLog);
