@@ -54,7 +54,7 @@ class Workload:
         self.msv, self.tl = (0, 12) if codec == "u16" else (255, 12)
         self.enc_kernels = {"huf": "huf_plan_kernel+huf_emit_kernel", "fse": "fse_encode_cta_kernel", "u16": "fse_encode_cta_kernel<U16>"}[codec]
         self.dec_kernels = {"huf": "huf_decode_kernel", "fse": "fse_decode_cta_kernel", "u16": "fse_decode_cta_kernel<U16>"}[codec]
-        self.launches_per_step = {"huf": 4, "fse": 2, "u16": 2}[codec]   # huf: plan, emit, decode, x2-fixup sweep
+        self.launches_per_step = {"huf": 5, "fse": 2, "u16": 2}[codec]   # huf: plan, emit, decode pass A, decode pass B (deferred list), x2 verdict sweep
 
     def describe(self, mib):
         if self.codec == "u16":
@@ -264,10 +264,12 @@ def measured_peak():
 
 
 def traffic_note(kernel):
-    """dram bytes per launch from the committed ncu capture, if one exists for this kernel"""
+    """dram bytes per launch from the committed ncu capture of this same command (profiles/traffic.json names the capture it was
+    read from), if one exists for this kernel: ncu cannot run inside the timed region, so this is a recorded measurement, not a
+    live one -- the line says so in `traffic_source`."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t.get(kernel)
+        return t.get(kernel.split("(")[0])
     except Exception:
         return None
 
@@ -579,7 +581,9 @@ def run_b200(a):
     dom = max(kern, key=kern.get)
     roof = lambda ms: round(alg / (ms * 1e-3) / 1e9, 2)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": roof(kern[dom]), "peak": peak, "unit": "GB/s",
-                "frac": round(roof(kern[dom]) / peak, 4), "traffic": traffic_note(dom), "peak_source": peak_src,
+                "frac": round(roof(kern[dom]) / peak, 4), "traffic": traffic_note(dom),
+                "traffic_source": "profiles/traffic.json: ncu --set full capture of this command (dram__bytes_read.sum + dram__bytes_write.sum per launch), round 2" if traffic_note(dom) else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg,
                 "all_kernels": {k: {"ms": round(v, 4), "achieved": roof(v), "frac": round(roof(v) / peak, 4)} for k, v in kern.items()}}
     # ---- the reference's CPU path on this box's host cores, same run (N=1 only) ----
