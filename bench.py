@@ -483,11 +483,11 @@ def run_b200(a):
     #          i.e. two streams: piece k+1 goes out while piece k is decoded and piece k-1 comes back. ----
     sg = None
     if dist is not None and world > 1 and not a.no_sg and a.codec == "huf":
-        # pieces: a decode launch costs about one "round" (0.95 ms) however small the batch, because every lane walks a whole stream;
-        # so cut no finer than what keeps a piece's decode under the time the root needs to take the previous piece back
-        # ((N-1) * piece / 770 GB/s): 1 piece at N=2, 4 at N=4, 8 at N=8.
+        # pieces: a decode launch lasts one "round" -- about 0.5 ms for a piece of <= 512 MiB (the decoder packs small batches into few
+        # CTAs), 0.95 ms for a GiB -- so cut no finer than what keeps a piece's decode under the time the root needs to take the
+        # previous piece back, (N-1) * piece / 770 GB/s:  K <= 2.8 (N-1), i.e. 2 pieces at N=2, 8 at N=4 and N=8.
         K = 1
-        while K < 8 and 2 * K <= (world - 1) * 1.4 and nb % (2 * K) == 0:
+        while K < 8 and 2 * K <= 2.8 * (world - 1) and nb % (2 * K) == 0:
             K *= 2
         nbk = nb // K                                               # blocks per piece
         wmax = cs.max().reshape(1).clone()
