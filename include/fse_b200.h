@@ -40,6 +40,8 @@ extern "C" {
  * does when dOrig != NULL (HUF additionally handles cSize==origSize / cSize==1 itself, lib/huf.h:60-63).
  * For the U16 codec sizes are in BYTES (a block holds blockSize/2 symbols, bench.c:221).
  * All pointers are device pointers; `stream` is a cudaStream_t (NULL = default stream).
+ * The compressed buffer must be readable for 32 bytes past the last block's compressed bytes (the decoders load aligned 16- / 32-byte
+ * pieces; what lies beyond a block's own bytes is never interpreted) -- bench.c's own buffer of nbChunks * FSE_compressBound() has it.
  * Return value: 0, or an error code if the launch itself could not be made.
  * ------------------------------------------------------------------------------------------------ */
 size_t FSEB200_HUF_compress_batch(void* dCBuf, size_t slot, size_t* dCSizes, const void* dSrc, size_t srcTotal,

@@ -24,14 +24,24 @@ def test_reference_arm_prints_one_contract_line():
     assert d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
 
 
-def test_committed_b200_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")))
+def _check_b200_line(d, launches_per_step):
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
-    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "u8" and d["bit_exact"] is True and d["roundtrip_ok"] is True
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] in ("u8", "u16") and d["bit_exact"] is True and d["roundtrip_ok"] is True
     r = d["roofline"]
     assert set(r) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
-    assert r["traffic"] and 0.9 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 2.0      # both kernels of the pair read the source: <= 2x
+    assert r["traffic"] is None or 0.9 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 2.0      # both kernels of the Huff0 encode pair read the source: <= 2x
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 2 ** 30
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "reference"
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and not d["clocks"]["reasons"]
-    assert d["gpu_launches"] == 3 * d["steps"]
+    assert d["gpu_launches"] == launches_per_step * d["steps"]
     assert d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+
+
+def test_committed_b200_lines_have_the_contract_keys():
+    """round 1's headline line, and round 2's lines for BASELINE configs[1], [2] and [4] (all blocks compared with the reference)"""
+    _check_b200_line(json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json"))), 3)
+    for name, launches in (("r02_bench_huf_p14_n1.json", 5), ("r02_bench_fse_p80_n1.json", 2), ("r02_bench_u16_p50_n1.json", 2)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        _check_b200_line(d, launches)
+        assert d["bit_exact_detail"]["blocks_compared"] == d["bit_exact_detail"]["of_blocks"] == d["config"]["blocks_per_gpu"]
+        assert d["bit_exact_detail"]["gpu_decodes_checker_output"] is True
