@@ -51,16 +51,21 @@ struct __align__(16) Plan {        // per block, in global scratch
 // kernel 1: statistics, code table, tree header, stream sizes, verdict -- one warp per block
 // ---------------------------------------------------------------------------------------------
 constexpr int PLAN_WARPS = 8;
-struct PlanWarp {
+struct PlanWarp {                  // 10.5 KB per warp, eight warps per CTA, two CTAs per SM.  More blocks in flight do not help: four warps per
+                                   // CTA (five CTAs, 20 blocks per SM) measured 1.41 instead of 1.37 ms per GiB for the pair -- the kernel is
+                                   // bound by its shared-memory atomics (LSU 55 %), not by the latency of the serial chains.  Packing two
+                                   // 16-bit counters per word (24 in flight) loses the warp-aggregated ATOMS.POPC.INC the compiler emits
+                                   // for a constant increment of 1: 1.81 ms, and 3.76 ms on P80 (26 lanes on one counter).
     u32   count4[4][256];          // one histogram per stream: stream sizes follow from them without touching the data again
     u32   count[256];
-    HNode nodes[2 * 256 + 2];
+    HNode nodes[2 * 256 + 2];      // tree nodes during HUF_buildCTable; the header writer's scratch (1.5 KB) afterwards
     u32   ctable[256];
     u32   firstVal[32];         // first code value per length + running per-length counters
     u8    lenOf[256];
     alignas(4) u8 header[136];
-    u32   wksp[384];
 };
+static_assert(sizeof(HNode) * (2 * 256 + 2) >= 384 * sizeof(u32), "header scratch must fit in the node array");
+__device__ __forceinline__ u32 seg_count(const PlanWarp& w, u32 k, u32 i) { return w.count4[k][i]; }
 
 // histogram of src[begin, end) into cnt[256] (shared memory), one warp
 __device__ __forceinline__ void warp_hist_range(u32* cnt, const u8* s, u32 begin, u32 end, unsigned lane)
@@ -169,7 +174,7 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     __syncwarp();
     u32 top = 0, best = 0;
     for (u32 i = lane; i < 256; i += 32) {
-        u32 const c = w.count4[0][i] + w.count4[1][i] + w.count4[2][i] + w.count4[3][i];
+        u32 const c = seg_count(w, 0, i) + seg_count(w, 1, i) + seg_count(w, 2, i) + seg_count(w, 3, i);
         w.count[i] = c;
         if (c) top = i; best = c > best ? c : best;
     }
@@ -188,9 +193,11 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
         huffLog = (u32)mb;
     }
     // ---- tree header (huf_compress.c:703-716) ----
+    __syncwarp();
+    u32* const wksp = reinterpret_cast<u32*>(w.nodes);                  // the tree is done with its nodes
     u64 hs = 0;
-    if (serialHeader) { if (lane == 0) hs = d_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, w.wksp); hs = __shfl_sync(FULL, hs, 0); }
-    else hs = warp_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, w.wksp);
+    if (serialHeader) { if (lane == 0) hs = d_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, wksp); hs = __shfl_sync(FULL, hs, 0); }
+    else hs = warp_huf_write_ctable(w.header, cap < sizeof(w.header) ? cap : sizeof(w.header), w.ctable, msv, huffLog, wksp);
     if (is_err(hs)) FSEB_FINAL(hs);
     if (hs + 12 >= n) FSEB_FINAL(0);
     u64 const capLeft = cap - hs;
@@ -201,7 +208,7 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
     #pragma unroll
     for (int k = 0; k < 4; k++) {
         u32 acc = 0;
-        for (u32 i = lane; i <= msv; i += 32) acc += w.count4[k][i] * (w.ctable[i] >> 16);
+        for (u32 i = lane; i <= msv; i += 32) acc += seg_count(w, k, i) * (w.ctable[i] >> 16);
         #pragma unroll
         for (int dlt = 16; dlt; dlt >>= 1) acc += __shfl_xor_sync(FULL, acc, dlt);
         bits[k] = acc;
@@ -451,7 +458,7 @@ huf_sizes_kernel(BatchGeom g, u64* __restrict__ csizes, const u8* __restrict__ s
 {
     __shared__ u8 nbOf[256];
     unsigned const lane = threadIdx.x & 31u;
-    nbOf[threadIdx.x] = (u8)(ct[threadIdx.x] >> 16);
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) nbOf[i] = (u8)(ct[i] >> 16);
     __syncthreads();
     u32 const b = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
     if (b >= g.nBlocks) return;
