@@ -305,6 +305,38 @@ def test_large_roundtrip_property(codec, p, mib):
         assert np.array_equal(got[b * SLOT: b * SLOT + int(wcs[b])], wc[b * SLOT: b * SLOT + int(wcs[b])])
 
 
+@pytest.mark.parametrize("codec,mib", [("huf", 256), ("fse", 256), ("u16", 256)])
+def test_full_compare_at_256mib(codec, mib):
+    """BASELINE configs[1] / [2] / [4] at 256 MiB: EVERY block's return value and compressed bytes against the compiled reference
+    (its pthread block loop, oracle/ref_shim.c), the GPU decoding the reference's blocks, and the identity round trip."""
+    lib, isref = checker()
+    if not isref:
+        pytest.skip("needs the compiled reference")
+    n = mib << 20
+    if codec == "u16":
+        data = gen_u16(n // 2, 240, 0.50, 1).view(np.uint8); slot, msv, tl = 32768, 0, 12
+    else:
+        data = probagen(n, 0.14 if codec == "huf" else 0.80); slot, msv, tl = SLOT, 255, 12
+    nb = n // BLOCK
+    wc, wcs, _ = cpu_compress(codec, data, slot=slot, msv=msv, tl=tl)
+    d = _dev(data)
+    cbuf, cs = ENC[codec](d, BLOCK, slot, msv, tl)
+    out, res = DEC[codec](cbuf, cs, n, BLOCK, slot, orig=d)
+    o2, r2 = DEC[codec](_dev(wc), _dev(wcs), n, BLOCK, slot, orig=d)        # the reference's blocks through our decoder
+    torch.cuda.synchronize()
+    assert torch.equal(out, d) and torch.equal(o2, d)
+    assert np.array_equal(cs.cpu().numpy().view(np.uint64), wcs)
+    got = cbuf[:nb * slot].cpu().numpy().reshape(nb, slot); want = wc[:nb * slot].reshape(nb, slot)
+    sizes = wcs.astype(np.int64); sizes[wcs > np.uint64(1 << 62)] = 0
+    if codec != "huf":
+        sizes[sizes == 1] = 0
+    cols = np.arange(slot, dtype=np.int64)[None, :]
+    for c0 in range(0, nb, 1024):
+        bad = (got[c0:c0 + 1024] != want[c0:c0 + 1024]) & (cols < sizes[c0:c0 + 1024, None])
+        assert not bad.any(), (codec, c0 + int(np.argwhere(bad)[0][0]))
+    assert int(sizes.sum()) > n // 20
+
+
 def test_raw_and_rle_tables_through_payload_calls():
     """FSE_buildCTable_raw/_rle + FSE_buildDTable_raw/_rle images driven through FSE_compress_usingCTable /
     FSE_decompress_usingDTable on the GPU vs the compiled reference (fullbench.c:595-629 call pattern)"""
