@@ -243,12 +243,23 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
 // ---------------------------------------------------------------------------------------------
 constexpr int THREADS = 128;
 
+// A 16-byte piece of a stream window that touches the stream's first or last bytes: only local bytes [a0, endByte) belong to
+// this stream (the neighbours are another warp's), so it goes out byte by byte.  Out of line: once or twice per stream.
+__device__ __noinline__ void store_piece_exact(u32* gw, u32 j, uint4 v, u32 a0, u32 endByte)
+{
+    u32 const wd[4] = { v.x, v.y, v.z, v.w };
+    u8* const pb = reinterpret_cast<u8*>(gw + j);
+    for (u32 t = 0; t < 16; t++) { u32 const at = 4 * j + t; if (at >= a0 && at < endByte) pb[t] = (u8)(wd[t >> 2] >> (8 * (t & 3))); }
+}
+
 __global__ void __launch_bounds__(THREADS)
 huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans, const u32* __restrict__ sharedCT)
 {
     constexpr u32 W = 256;                                          // words of stream window per warp (a group adds <= 88, < 32 wait for the next flush)
-    __shared__ uint2 ctab[256];                                     // cells {code, nbBits}: one 8-byte load, no unpacking
-    __shared__ u32 winAll[4 * W];
+    __shared__ u32 ctab[256];                                       // cells nbBits | code << 8.  4-byte cells: the kernel is bound by shared-memory
+                                                                    // wavefronts (ncu: 95 % of the data pipe), and an 8-byte cell per lane costs two
+    constexpr u32 WP = W + 4;                                       // + 2 spill words (a put writes 3 consecutive words, never wrapping) + 2 unused
+    __shared__ __align__(16) u32 winAll[4 * WP];
     int const tid = threadIdx.x;
     unsigned const lane = tid & 31u; int const k = tid >> 5;
     u32 const b = blockIdx.x;
@@ -261,9 +272,9 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
 
     {   const u32* const ct = sharedCT ? sharedCT : P.ctable;       // one caller-supplied table for the whole batch, or the block's own
         u32 const c0 = ct[tid], c1 = ct[tid + 128];
-        ctab[tid] = make_uint2(c0 & 0xFFFFu, c0 >> 16); ctab[tid + 128] = make_uint2(c1 & 0xFFFFu, c1 >> 16);
+        ctab[tid] = (c0 >> 16) | (c0 << 8 & 0xFFFF00u); ctab[tid + 128] = (c1 >> 16) | (c1 << 8 & 0xFFFF00u);
     }
-    for (u32 i = tid; i < 4 * W; i += THREADS) winAll[i] = 0;
+    for (u32 i = tid; i < 4 * WP; i += THREADS) winAll[i] = 0;
     // tree header and jump table straight to the block (byte stores: the word they end in is shared with stream 1)
     for (u32 i = tid; i < hSize; i += THREADS) d[i] = P.header[i];
     if (tid < 3) { u32 const v = P.streamBytes[tid]; d[hSize + 2 * tid] = (u8)v; d[hSize + 2 * tid + 1] = (u8)(v >> 8); }
@@ -272,22 +283,27 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
         u32 const seg = (n + 3) / 4;
         int const segBeg = (int)(k * seg);
         int const segEnd = (k < 3) ? (int)((k + 1) * seg) : (int)n;
-        u32 const sTab = (u32)__cvta_generic_to_shared(ctab);
+        u32 sTab = (u32)__cvta_generic_to_shared(ctab);
+        asm volatile("mov.u32 %0, %0;" : "+r"(sTab));               // keep it in a register (otherwise re-derived from the CTA id before every look-up)
         // The stream is built in a circular window of aligned 32-bit words of the destination and flushed as it grows, so a
         // CTA needs 6 KB of shared memory instead of an image of the whole block (occupancy: 10+ CTAs per SM instead of 6).
-        u32* const win = winAll + k * W;
-        u32 const sWin = (u32)__cvta_generic_to_shared(win);
+        u32* const win = winAll + k * WP;
+        u32 sWin = (u32)__cvta_generic_to_shared(win);
+        asm volatile("mov.u32 %0, %0;" : "+r"(sWin));
         u8* const gstart = d + P.streamOff[k];
-        u32 const a0 = (u32)(reinterpret_cast<u64>(gstart) & 3);
+        u32 const a0 = (u32)(reinterpret_cast<u64>(gstart) & 15);   // the window is 16-byte aligned in the destination: it is flushed in 16-byte pieces
         u32* const gw = reinterpret_cast<u32*>(gstart - a0);        // word j of the window <-> gw[j]
         u32 const sBytes = (k < 3) ? P.streamBytes[k] : total - P.streamOff[3];
         u32 const endByte = a0 + sBytes;                            // stream occupies local bytes [a0, endByte)
         u32 bitpos = 8u * a0;
         u32 flushed = 0;                                            // words already written out
-        auto lds64 = [&](u32 a) -> uint2 { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; };
+        auto lds32 = [&](u32 a) -> u32 { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+        auto lds64 = [&](u32 o) -> uint2 { u32 const e = lds32(sTab + (o >> 1)); return make_uint2(e >> 8, e & 0xFFu); };   // {code, nbBits} of the cell at 8 * symbol
         auto red_or = [&](u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); };
-        auto red_or_nz = [&](u32 a, u32 v) {                        // predicated, not branched
-            asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0], %1; }" :: "r"(a), "r"(v) : "memory");
+        // three consecutive words, unconditionally: a predicated red compiles to a branch around it (4 more instructions each,
+        // 162 instructions per 8 symbols in all), and a zero operand costs the shared-memory pipe no more than a one-lane red
+        auto red_or3 = [&](u32 a, u32 v0, u32 v1, u32 v2) {
+            asm volatile("red.shared.or.b32 [%0], %1; red.shared.or.b32 [%0+4], %2; red.shared.or.b32 [%0+8], %3;" :: "r"(a), "r"(v0), "r"(v1), "r"(v2) : "memory");
         };
         // warp scan of the lanes' bit counts: exclusive prefix in `excl`, returns the warp total
         auto scan = [&](u32 held, u32& excl) -> u32 {
@@ -298,31 +314,29 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             excl = incl - held;
             return __shfl_sync(FULL, incl, 31);
         };
-        // ORs up to 64 bits (a0 | a1 << 32) into the window at bit offset `at`
+        // ORs up to 64 bits (a0 | a1 << 32) into the window at bit offset `at`.  Only the first word's position wraps: words
+        // W and W+1 of the window are spill cells for words 0 and 1 of the next lap, folded in when those are flushed.
         auto put = [&](u32 at, u32 x0, u32 x1) {
-            u32 const j = at >> 5, sh = at & 31;
-            red_or_nz(sWin + 4 * (j & (W - 1)), x0 << sh);
-            red_or_nz(sWin + 4 * ((j + 1) & (W - 1)), __funnelshift_l(x0, x1, sh));
-            red_or_nz(sWin + 4 * ((j + 2) & (W - 1)), __funnelshift_l(x1, 0, sh));
+            u32 const sh = at & 31;
+            red_or3(sWin + ((at >> 3) & (4 * (W - 1))), x0 << sh, __funnelshift_l(x0, x1, sh), __funnelshift_l(x1, 0, sh));
         };
-        // writes out window words [flushed, upTo) that are final; word 0 and the last word may be shared with a neighbour
-        auto store_word = [&](u32 j, u32 v) {
-            u32 const lo = 4 * j, hi = 4 * j + 4;
-            if (lo >= a0 && hi <= endByte) gw[j] = v;
-            else { u8* const pb = reinterpret_cast<u8*>(gw + j); for (u32 t = 0; t < 4; t++) if (lo + t >= a0 && lo + t < endByte) pb[t] = (u8)(v >> (8 * t)); }
-        };
+        // Final words leave 128 at a time, one 16-byte piece per lane (the 32-words-per-flush version spent 50 of 135
+        // instructions per 8 symbols here).  Between flushes < 128 final words wait, a group adds <= 88 (+ 2 spill): < W.
         auto flush = [&](bool all) {
             u32 const upTo = all ? (endByte + 3) / 4 : (bitpos >> 5);
-            if (!all && flushed + 32 > upTo) return;                // warp-uniform: fewer than 32 final words pending
+            if (!all && flushed + 128 > upTo) return;               // warp-uniform
             __syncwarp();
-            while (all ? flushed < upTo : flushed + 32 <= upTo) {
-                u32 const j = flushed + lane;
+            while (all ? flushed < upTo : flushed + 128 <= upTo) {
+                u32 const j = flushed + 4 * lane;
                 if (j < upTo) {
-                    u32 const v = win[j & (W - 1)]; win[j & (W - 1)] = 0;
-                    if (!all && (j != 0 || a0 == 0)) gw[j] = v;     // interior word: every bit below bitpos is final and inside the stream
-                    else store_word(j, v);                          // first / last word: byte-exact
+                    u32 const i = j & (W - 1);
+                    uint4 v = *reinterpret_cast<uint4*>(win + i);
+                    *reinterpret_cast<uint4*>(win + i) = make_uint4(0, 0, 0, 0);
+                    if (i == 0) { v.x |= win[W]; v.y |= win[W + 1]; win[W] = 0; win[W + 1] = 0; }
+                    if (!all && (j != 0 || a0 == 0)) *reinterpret_cast<uint4*>(gw + j) = v;   // interior piece: below bitpos, inside the stream
+                    else store_piece_exact(gw, j, v, a0, endByte);  // first / last pieces
                 }
-                flushed += 32;
+                flushed += 128;
             }
         };
         auto place = [&](u32 x0, u32 x1, u32 held) -> u32 {         // lane's `held` bits go to bitpos + exclusive prefix
@@ -339,12 +353,13 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             int const nBig = al8 ? (segEnd - segBeg) / 256 : 0;
             const uint2* gq = reinterpret_cast<const uint2*>(s + segEnd) - 1 - lane;         // group j: piece gq[-32 j]
             auto half = [&](u32 w, u32& a0, u32& a1) -> u32 {        // 4 symbols of one word -> up to 44 bits
-                uint2 const e0 = lds64(sTab + 8 * (w >> 24)), e1 = lds64(sTab + 8 * __byte_perm(w, 0, 0x4442));
-                uint2 const e2 = lds64(sTab + 8 * __byte_perm(w, 0, 0x4441)), e3 = lds64(sTab + 8 * (w & 0xFFu));
-                u32 const p01 = e0.x | (e1.x << e0.y), l01 = e0.y + e1.y;
-                u32 const p23 = e2.x | (e3.x << e2.y), l23 = e2.y + e3.y;
-                a0 = p01 | (p23 << l01); a1 = __funnelshift_l(p23, 0, l01);
-                return l01 + l23;
+                // a cell is used as a shift amount as it is: the funnel shift takes the low 5 bits (lengths <= 11, pairs <= 22)
+                u32 const e0 = lds32(sTab + 4 * __byte_perm(w, 0, 0x4443)), e1 = lds32(sTab + 4 * __byte_perm(w, 0, 0x4442));
+                u32 const e2 = lds32(sTab + 4 * __byte_perm(w, 0, 0x4441)), e3 = lds32(sTab + 4 * __byte_perm(w, 0, 0x4440));
+                u32 const p01 = (e0 >> 8) | __funnelshift_l(0, e1 >> 8, e0), l01 = e0 + e1;
+                u32 const p23 = (e2 >> 8) | __funnelshift_l(0, e3 >> 8, e2), l23 = e2 + e3;
+                a0 = p01 | __funnelshift_l(0, p23, l01); a1 = __funnelshift_l(p23, 0, l01);
+                return (l01 + l23) & 0xFFu;
             };
             auto big = [&](uint2 cur) {
                 u32 x0, x1, y0, y1;
@@ -382,7 +397,7 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
         {
             const u32* gp = reinterpret_cast<const u32*>(s + hiCur) - 1 - lane;             // group j: word gp[-32 j]
             auto group = [&](u32 o0, u32 o1, u32 o2, u32 o3) {      // table offsets of the 4 symbols, emission order
-                uint2 const e0 = lds64(sTab + o0), e1 = lds64(sTab + o1), e2 = lds64(sTab + o2), e3 = lds64(sTab + o3);
+                uint2 const e0 = lds64(o0), e1 = lds64(o1), e2 = lds64(o2), e3 = lds64(o3);
                 u32 const p01 = e0.x | (e1.x << e0.y), l01 = e0.y + e1.y;           // <= 22 bits
                 u32 const p23 = e2.x | (e3.x << e2.y), l23 = e2.y + e3.y;
                 u32 const a0 = p01 | (p23 << l01), a1 = __funnelshift_l(p23, 0, l01);
@@ -435,7 +450,7 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                 u64 acc = 0; u32 held = 0;                          // up to 48 bits
                 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    uint2 const e = lds64(sTab + 8 * ((cur >> (8 * (3 - j))) & 0xFF));
+                    uint2 const e = lds64(8 * ((cur >> (8 * (3 - j))) & 0xFF));
                     if (j < nValid) { acc |= (u64)e.x << held; held += e.y; }
                 }
                 bitpos += place((u32)acc, (u32)(acc >> 32), held);
