@@ -255,10 +255,10 @@ __device__ __noinline__ void store_piece_exact(u32* gw, u32 j, uint4 v, u32 a0, 
 __global__ void __launch_bounds__(THREADS)
 huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, const Plan* __restrict__ plans, const u32* __restrict__ sharedCT)
 {
-    constexpr u32 W = 256;                                          // words of stream window per warp (a group adds <= 88, < 32 wait for the next flush)
+    constexpr u32 W = 512;                                          // words of stream window per warp (a double group adds <= 176, < 128 wait for the next flush)
     __shared__ u32 ctab[256];                                       // cells nbBits | code << 8.  4-byte cells: the kernel is bound by shared-memory
                                                                     // wavefronts (ncu: 95 % of the data pipe), and an 8-byte cell per lane costs two
-    constexpr u32 WP = W + 4;                                       // + 2 spill words (a put writes 3 consecutive words, never wrapping) + 2 unused
+    constexpr u32 WP = W + 4;                                       // + 3 spill words (a put writes up to 4 consecutive words, never wrapping) + 1 unused
     __shared__ __align__(16) u32 winAll[4 * WP];
     int const tid = threadIdx.x;
     unsigned const lane = tid & 31u; int const k = tid >> 5;
@@ -315,13 +315,20 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             return __shfl_sync(FULL, incl, 31);
         };
         // ORs up to 64 bits (a0 | a1 << 32) into the window at bit offset `at`.  Only the first word's position wraps: words
-        // W and W+1 of the window are spill cells for words 0 and 1 of the next lap, folded in when those are flushed.
+        // W .. W+2 of the window are spill cells for words 0 .. 2 of the next lap, folded in when those are flushed.
         auto put = [&](u32 at, u32 x0, u32 x1) {
             u32 const sh = at & 31;
             red_or3(sWin + ((at >> 3) & (4 * (W - 1))), x0 << sh, __funnelshift_l(x0, x1, sh), __funnelshift_l(x1, 0, sh));
         };
+        // the same for up to 88 bits (z0 | z1 << 32 | z2 << 64): four words
+        auto put96 = [&](u32 at, u32 z0, u32 z1, u32 z2) {
+            u32 const sh = at & 31;
+            asm volatile("red.shared.or.b32 [%0], %1; red.shared.or.b32 [%0+4], %2; red.shared.or.b32 [%0+8], %3; red.shared.or.b32 [%0+12], %4;"
+                         :: "r"(sWin + ((at >> 3) & (4 * (W - 1)))), "r"(z0 << sh), "r"(__funnelshift_l(z0, z1, sh)), "r"(__funnelshift_l(z1, z2, sh)),
+                            "r"(__funnelshift_l(z2, 0, sh)) : "memory");
+        };
         // Final words leave 128 at a time, one 16-byte piece per lane (the 32-words-per-flush version spent 50 of 135
-        // instructions per 8 symbols here).  Between flushes < 128 final words wait, a group adds <= 88 (+ 2 spill): < W.
+        // instructions per 8 symbols here).  Between flushes < 128 final words wait, a double group adds <= 176 (+ 3 spill): < W.
         auto flush = [&](bool all) {
             u32 const upTo = all ? (endByte + 3) / 4 : (bitpos >> 5);
             if (!all && flushed + 128 > upTo) return;               // warp-uniform
@@ -332,7 +339,7 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                     u32 const i = j & (W - 1);
                     uint4 v = *reinterpret_cast<uint4*>(win + i);
                     *reinterpret_cast<uint4*>(win + i) = make_uint4(0, 0, 0, 0);
-                    if (i == 0) { v.x |= win[W]; v.y |= win[W + 1]; win[W] = 0; win[W + 1] = 0; }
+                    if (i == 0) { v.x |= win[W]; v.y |= win[W + 1]; v.z |= win[W + 2]; win[W] = 0; win[W + 1] = 0; win[W + 2] = 0; }
                     if (!all && (j != 0 || a0 == 0)) *reinterpret_cast<uint4*>(gw + j) = v;   // interior piece: below bitpos, inside the stream
                     else store_piece_exact(gw, j, v, a0, endByte);  // first / last pieces
                 }
@@ -361,13 +368,27 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
                 a0 = p01 | __funnelshift_l(0, p23, l01); a1 = __funnelshift_l(p23, 0, l01);
                 return (l01 + l23) & 0xFFu;
             };
-            auto big = [&](uint2 cur) {
-                u32 x0, x1, y0, y1;
-                u32 const lx = half(cur.y, x0, x1), ly = half(cur.x, y0, y1);       // .y holds the higher addresses: emitted first
-                u32 excl; u32 const sum = scan(lx + ly, excl);
-                put(bitpos + excl, x0, x1);
-                put(bitpos + excl + lx, y0, y1);
-                bitpos += sum;
+            // Z = X | Y << lx for two halves (X < 2^lx, lx <= 44, Y < 2^44): the lane's 8 symbols as one string of <= 88 bits, so
+            // that they cost 4 window ORs instead of 6 -- the kernel is bound by shared-memory wavefronts, not by instructions
+            auto merge = [&](u32 x0, u32 x1, u32 lx, u32 y0, u32 y1, u32& z0, u32& z1, u32& z2) {
+                u32 const t0 = __funnelshift_l(0, y0, lx), t1 = __funnelshift_l(y0, y1, lx), t2 = __funnelshift_l(y1, 0, lx);   // Y << (lx & 31)
+                bool const far = (lx & 32u) != 0;
+                z0 = x0 | (far ? 0u : t0); z1 = x1 | (far ? t0 : t1); z2 = far ? t1 : t2;
+            };
+            // Two groups of 256 symbols per scan: the two bit counts ride in the halves of one register (each total < 2^16).
+            auto big2 = [&](uint2 curA, uint2 curB) {
+                u32 x0, x1, y0, y1, za0, za1, za2, zb0, zb1, zb2;
+                u32 lx = half(curA.y, x0, x1), ly = half(curA.x, y0, y1);           // .y holds the higher addresses: emitted first
+                merge(x0, x1, lx, y0, y1, za0, za1, za2);
+                u32 const la = lx + ly;
+                lx = half(curB.y, x0, x1); ly = half(curB.x, y0, y1);
+                merge(x0, x1, lx, y0, y1, zb0, zb1, zb2);
+                u32 const lb = lx + ly;
+                u32 excl; u32 const sum = scan(la | (lb << 16), excl);
+                u32 const sumA = sum & 0xFFFFu;
+                put96(bitpos + (excl & 0xFFFFu), za0, za1, za2);
+                put96(bitpos + sumA + (excl >> 16), zb0, zb1, zb2);
+                bitpos += sumA + (sum >> 16);
                 flush(false);
             };
             constexpr int PB = 2;                                   // pieces in flight per register set (2 x 256 B per warp)
@@ -377,13 +398,9 @@ huf_emit_kernel(BatchGeom g, u8* __restrict__ cbuf, const u8* __restrict__ src, 
             for (int i = 0; i < PB; i++) { bufA[i] = rounds > 0 ? __ldg(gq - 32 * i) : make_uint2(0, 0); bufB[i] = make_uint2(0, 0); }
             auto round = [&](uint2 (&X)[PB], uint2 (&Y)[PB], int r) {
                 gq -= 32 * PB;
-                bool const more = r + 1 < rounds;
-                #pragma unroll
-                for (int i = 0; i < PB; i++) {
-                    uint2 const cur = X[i];
-                    if (more) Y[i] = __ldg(gq - 32 * i);
-                    big(cur);
-                }
+                uint2 const c0 = X[0], c1 = X[1];
+                if (r + 1 < rounds) { Y[0] = __ldg(gq); Y[1] = __ldg(gq - 32); }
+                big2(c0, c1);
             };
             int r = 0;
             #pragma unroll 1
