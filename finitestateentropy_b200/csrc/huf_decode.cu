@@ -172,10 +172,11 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     // block whose smallest table does not fit that budget is not decoded but appended to deferList.  Pass B (deferList == nullptr)
     // walks that list with a larger budget (fewer CTAs per SM); what does not fit even there takes the per-symbol path.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u16* const tbl = reinterpret_cast<u16*>(smem_raw);                                   // [rows][G]
-    unsigned char* const ringRaw = smem_raw + rows * (G * 2);
+    // The ring comes first: its address is then (compile-time base) + an offset the hot loop builds with one OR.
+    unsigned char* const ringRaw = smem_raw;
     BuildScratch& bs = *reinterpret_cast<BuildScratch*>(ringRaw);
     Facts& fx = *reinterpret_cast<Facts*>(ringRaw + RING_BYTES);
+    u16* const tbl = reinterpret_cast<u16*>(smem_raw + RING_BYTES + sizeof(Facts));      // [rows][G]
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     u32 const blk0 = blockIdx.x * gEff;
     u32 const nWork = list ? *listCount : g.nBlocks;
@@ -288,7 +289,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     };
 
     u32 w0 = 0, w1 = 0, w2 = 0, r = 0;               // raw stream words: the window starts at bit r of w0 and spans w0..w2
-    u32 ctr = 0;                                      // ring read cursor: (ctr >> 29) = slot of the next word to fetch
+    u32 kBase = 0;                                    // absolute index of the next stream word to fetch = kBase + (r >> 5): `r` is never reduced
     u32 q = 0;                                        // next chunk to enter the ring (chunks 0..q-1 are consumed or in it); chunk q -> slots (4q..4q+3) mod 8
     auto store_next = [&]() {                         // chunk q out of the pending pair; an odd q uses the pair up: fetch the next one
         u32 const a = ringLane + (q & 1) * (4 * THREADS * 4);
@@ -305,13 +306,8 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     // slot numbers alone, and the ring never runs dry whatever the code lengths.  On typical data only the group-start
     // check stores, so a load has 16 symbols of work to land before the next store of this WARP touches its registers (the
     // scoreboard is per warp, not per lane: a store every 8 symbols exposed the latency).
-    auto unread = [&]() -> u32 { return ((4 * q - (ctr >> 29) - 1) & 7) + 1; };
+    auto unread = [&]() -> u32 { return 4 * q - kBase - (r >> 5); };
     auto top_up = [&](u32 threshold) { if (unread() <= threshold) store_next(); };
-    auto fetch_word = [&]() -> u32 {
-        u32 const v = lds_u32(ringLane + __umulhi(ctr, RW * THREADS * 4));
-        ctr += 1u << 29;
-        return v;
-    };
 
     if (go) {                                         // the first pair fills the ring, the window words come out of it
         u32 const k0 = c0 >> 5;                       // first word of the window: 0..8
@@ -319,10 +315,14 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
         q = 2 * (k0 >> 3);
         load_pair(q >> 1);
         store_next(); store_next();                   // ring full: words 4q-8 .. 4q-1; the next pair is on its way
-        ctr = (k0 & 7) << 29;
-        w0 = fetch_word(); if (!(ctr >> 29)) store_next();      // wrapped to slot 0 = everything fetched: the next chunk goes there
-        w1 = fetch_word(); if (!(ctr >> 29)) store_next();
-        w2 = fetch_word(); if (!(ctr >> 29)) store_next();
+        kBase = k0;
+        auto fetch_word = [&]() -> u32 {              // word kBase lives in slot kBase & 7
+            u32 const v = lds_u32(ringLane + (kBase & 7) * (THREADS * 4));
+            kBase++;
+            if (!(kBase & 7)) store_next();           // wrapped to slot 0 = everything fetched: the next chunk goes there
+            return v;
+        };
+        w0 = fetch_word(); w1 = fetch_word(); w2 = fetch_word();
         top_up(4);                                    // bring the ring to >= 5 unread words
     }
 
@@ -330,14 +330,19 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     u32 const tblCol = (u32)__cvta_generic_to_shared(tbl) + col * 2;       // + row * 128
     u32 const M = fx.mbits[col];
     u32 const shX = 32 - (tl ? tl : 1);                // window >> shX = index at full resolution
-    u32 const shY = 32 - (M ? M : 1);                  // window >> shY = first-level index
+    u32 const shY = 32 - (M ? M : 1);                // umulhi(window, mulY) = window >> (32 - M) = first-level index
     int const dOff = (int)fx.dOff[col];
     u32 const tblColD = tblCol + (u32)dOff * (G * 2);  // row = min(x - D, y) + D: the "+ D" lives in the base address
     bool const hardBlk = fx.hard[col] != 0;
 
+    static_assert(THREADS * 4 == 1024, "slot stride: (r >> 5) * 1024 = (r * 32) & ~1023");
+    u32 const tid4 = tid * 4;
+    u32 const ringBase = (u32)__cvta_generic_to_shared(ringRaw);
+    u32 const slotBias = kBase * (THREADS * 4);        // (kBase + (r >> 5)) * 1024, masked to the 8 slots: the low 10 bits of r * 32 fall to the mask
     u32 hi = __funnelshift_l(w1, w0, r), lo = __funnelshift_l(w2, w1, r);
-    // Row of the window: min(x, D + y) = min(x - D, y) + D, as a signed minimum.  Plain shifts, no IMAD.HI: the wide
-    // multiply issues at a fraction of the ALU rate and throttled the whole loop (ncu: math-pipe throttle, round 2 v1).
+    // Row of the window: min(x, D + y) = min(x - D, y) + D, as a signed minimum.  Plain shifts: a high multiply for one of them
+    // (to move work from the busy ALU pipe to the FMA pipe) measured 0.98 instead of 0.94 ms per GiB, both as IMAD.HI throttled
+    // that pipe outright (round 2 v1).
 #define HUFD_LOOKUP(E, H) do { \
         int const a_ = (int)((H) >> shX) - dOff; \
         int const y_ = (int)((H) >> shY); \
@@ -345,15 +350,19 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
     } while (0)
     // After a pair of symbols: `r` has grown by their bits (it is never reduced: the funnel shifts take it modulo 32 and
     // bit 5 FLIPS exactly when a 32-bit word has been used up -- a pair is at most 24 bits).  Then the words rotate and the
-    // next one comes out of the ring, all predicated; the window is recomputed from the raw words either way.
-#define HUFD_ADVANCE(ADDED) do { \
+    // next one comes out of the ring, all predicated; the window is recomputed from the raw words either way.  The slot of that
+    // next word follows from `r` itself -- word kBase + (r >> 5), slot = index mod 8 -- as one multiply-add (FMA pipe) and one
+    // AND-OR with the lane's column offset; the ring sits at the start of shared memory, so its base is an immediate of the load.
+    // `r` must stay a clean bit count for that: the pair's two lengths are added by one byte-wise dot product of the packed
+    // cells (len0 | sym0 << 8 | len1 << 16 | sym1 << 24) with 0x00010001 -- also on the FMA pipe.
+#define HUFD_ADVANCE(PACKED) do { \
         u32 const rOld_ = r; \
-        r += (ADDED); \
-        u32 const ra_ = ringLane + __umulhi(ctr, RW * THREADS * 4); \
+        r = __dp4a((u32)(PACKED), 0x00010001u, r); \
+        u32 const ra_ = ((rOld_ * 32u * (THREADS * 4 / 1024u) + slotBias) & ((RW - 1) * THREADS * 4)) | tid4; \
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t" \
-                     "xor.b32 t, %5, %6;\n\tand.b32 t, t, 32;\n\tsetp.ne.u32 p, t, 0;\n\t" \
-                     "@p mov.b32 %0, %1;\n\t@p mov.b32 %1, %2;\n\t@p ld.shared.u32 %2, [%4];\n\t@p add.u32 %3, %3, 0x20000000;\n\t}" \
-                     : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(ctr) : "r"(ra_), "r"(r), "r"(rOld_) : "memory"); \
+                     "xor.b32 t, %4, %5;\n\tand.b32 t, t, 32;\n\tsetp.ne.u32 p, t, 0;\n\t" \
+                     "@p mov.b32 %0, %1;\n\t@p mov.b32 %1, %2;\n\t@p ld.shared.u32 %2, [%3];\n\t}" \
+                     : "+r"(w0), "+r"(w1), "+r"(w2) : "r"(ringBase + ra_), "r"(r), "r"(rOld_) : "memory"); \
         hi = __funnelshift_l(w1, w0, r); lo = __funnelshift_l(w2, w1, r); \
     } while (0)
 
@@ -372,10 +381,12 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
                 else if ((h & 3) == 2 && __builtin_expect(__any_sync(__activemask(), unread() <= 3), 0)) top_up(3);   // mid-group: only when a lane ran low (lanes leave this loop at different trip counts: vote among those still in it)
                 u32 e0, e1, e2, e3, hi1;
                 HUFD_LOOKUP(e0, hi); hi1 = __funnelshift_l(lo, hi, e0); HUFD_LOOKUP(e1, hi1);
-                HUFD_ADVANCE(e0 + e1);
+                u32 const p01 = e0 | (e1 << 16);
+                HUFD_ADVANCE(p01);
                 HUFD_LOOKUP(e2, hi); hi1 = __funnelshift_l(lo, hi, e2); HUFD_LOOKUP(e3, hi1);
-                HUFD_ADVANCE(e2 + e3);
-                o[h] = __byte_perm(e0 | (e1 << 16), e2 | (e3 << 16), 0x7531);
+                u32 const p23 = e2 | (e3 << 16);
+                HUFD_ADVANCE(p23);
+                o[h] = __byte_perm(p01, p23, 0x7531);
             }
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                          :: "l"(outp + pos), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
@@ -398,7 +409,7 @@ huf_decode_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ cbuf
             u32 e;
             if (hardBlk) e = parked_cell(hi >> (32 - tl));
             else HUFD_LOOKUP(e, hi);
-            HUFD_ADVANCE(e & 0xFF);
+            HUFD_ADVANCE(e);
             outp[pos++] = (u8)(e >> 8);
         }
     }
