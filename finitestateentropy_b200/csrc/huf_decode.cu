@@ -89,6 +89,52 @@ __device__ __forceinline__ u32 canon_cell(const u16* rankEnd, const u16* listSta
     return (tl + 1 - w) | ((u32)sorted[k] << 8);
 }
 
+// HUF_readStats (lib/entropy_common.c:158-215) with the whole warp: same verdicts as d_huf_read_stats.  The raw 4-bit form and
+// the per-weight statistics are spread over the lanes (they were 7 % of this kernel's instructions on one lane); the
+// FSE-compressed form (a serial 2-state decode of <= 255 weights) stays on lane 0.  All lanes return the same value.
+__device__ u64 warp_huf_read_stats(u8* weights, u32* rankStats, u32* nbSymPtr, u32* tlPtr, const u8* in, u64 srcSize, unsigned lane)
+{
+    if (!srcSize) return err(E_SRC_WRONG);
+    u64 iSize = in[0], oSize;
+    if (iSize >= 128) {                                   // raw 4-bit weights (:167-177)
+        oSize = iSize - 127;
+        iSize = (oSize + 1) / 2;
+        if (iSize + 1 > srcSize) return err(E_SRC_WRONG);
+        if (oSize >= 256) return err(E_CORRUPT);
+        for (u32 k = lane; k < (u32)iSize; k += 32) { u8 const v = in[1 + k]; weights[2 * k] = v >> 4; weights[2 * k + 1] = v & 15; }
+    } else {                                              // FSE-compressed weights (:178-183)
+        if (iSize + 1 > srcSize) return err(E_SRC_WRONG);
+        oSize = 0;
+        if (lane == 0) oSize = d_huf_read_weights_fse(weights, 256, in, iSize);
+        oSize = __shfl_sync(FULL, oSize, 0);
+        if (is_err(oSize)) return oSize;
+    }
+    if (lane <= HUF_MAX_TLOG) rankStats[lane] = 0;
+    __syncwarp();
+    u32 total = 0; bool bad = false;
+    for (u32 n = lane; n < (u32)oSize; n += 32) {
+        u32 const w = weights[n];
+        if (w >= HUF_MAX_TLOG) bad = true;
+        else { atomicAdd(&rankStats[w], 1u); total += (1u << w) >> 1; }
+    }
+    if (__any_sync(FULL, bad)) return err(E_CORRUPT);
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+    if (total == 0) return err(E_CORRUPT);
+    u32 const tl = hibit(total) + 1;
+    if (tl > HUF_MAX_TLOG) return err(E_CORRUPT);
+    u32 const rest = (1u << tl) - total;
+    u32 const lastW = hibit(rest) + 1;
+    if ((1u << hibit(rest)) != rest) return err(E_CORRUPT);
+    __syncwarp();
+    if (lane == 0) { weights[oSize] = (u8)lastW; rankStats[lastW]++; }
+    __syncwarp();
+    if ((rankStats[1] < 2) || (rankStats[1] & 1)) return err(E_CORRUPT);
+    *tlPtr = tl;
+    *nbSymPtr = (u32)(oSize + 1);
+    return iSize + 1;
+}
+
 // Builds the unified table of block column `blk` with one warp.
 __device__ void setup_block(u16* tbl, Facts& fx, BuildScratch& bs, u32 rows, int blk, const u8* csrc, u64 csize, int warp)
 {
@@ -97,9 +143,9 @@ __device__ void setup_block(u16* tbl, Facts& fx, BuildScratch& bs, u32 rows, int
     u8* const sorted = bs.sorted[warp];
     u16* const rankEnd = bs.rankEnd[warp];
     u16* const listStart = bs.listStart[warp];
-    u32 nbSym = 0, tl = 0, M = 0, cut = 0, nRows = 0; u64 h = 0;
+    u32 nbSym = 0, tl = 0, M = 0, cut = 0, nRows = 0;
+    u64 h = warp_huf_read_stats(weights, bs.rankStats[warp], &nbSym, &tl, csrc, csize, lane);
     if (lane == 0) {
-        h = d_huf_read_stats(weights, 256, bs.rankStats[warp], &nbSym, &tl, csrc, csize);
         if (!is_err(h) && tl > HUF_MAX_TLOG) h = err(E_TLOG_TOO_LARGE);      // huf_decompress.c:143
         if (!is_err(h) && h >= csize) h = err(E_SRC_WRONG);                   // huf_decompress.c:426
         if (!is_err(h)) {
@@ -135,8 +181,6 @@ __device__ void setup_block(u16* tbl, Facts& fx, BuildScratch& bs, u32 rows, int
     }
     h = __shfl_sync(FULL, h, 0);
     if (is_err(h)) return;
-    nbSym = __shfl_sync(FULL, nbSym, 0);
-    tl = __shfl_sync(FULL, tl, 0);
     M = __shfl_sync(FULL, M, 0); cut = __shfl_sync(FULL, cut, 0); nRows = __shfl_sync(FULL, nRows, 0);
     __syncwarp();
     // sorted symbol list: stable by weight, then symbol order (huf_decompress.c:158-183 fills cells in that order)

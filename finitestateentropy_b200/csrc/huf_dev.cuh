@@ -26,6 +26,23 @@ __device__ inline u32 d_huf_select_decoder(u64 dstSize, u64 cSrcSize)
     return t1 < t0;
 }
 
+// The FSE-compressed form of the weights (entropy_common.c:178-183, FSE_decompress with tableLog <= 6): in[1 .. iSize] -> weights,
+// returns their number or an error.
+__device__ inline u64 d_huf_read_weights_fse(u8* weights, u64 hwSize, const u8* in, u64 iSize)
+{
+    short norm[FSE_MAX_SV + 1];
+    u32 dt[1 + 64];
+    u16 cellSym[64];
+    u16 nextOf[FSE_MAX_SV + 1];
+    unsigned tl = 0, msv = FSE_MAX_SV;
+    u64 const h = d_read_ncount(norm, &msv, &tl, in + 1, iSize);
+    if (is_err(h)) return h;
+    if (tl > 6) return err(E_TLOG_TOO_LARGE);
+    u64 const r = d_build_dtable_serial<false>(dt, norm, msv, tl, FSE_MAX_SV, FSE_MAX_TLOG, cellSym, nextOf);
+    if (is_err(r)) return r;
+    return d_fse_decode_serial(weights, hwSize - 1, in + 1 + h, iSize - h, dt);
+}
+
 // weights: u8[hwSize] (hwSize = 256), rankStats: u32[13].  Returns header bytes consumed or an error.
 __device__ inline u64 d_huf_read_stats(u8* weights, u64 hwSize, u32* rankStats, u32* nbSymPtr, u32* tlPtr,
                                        const u8* in, u64 srcSize)
@@ -43,17 +60,7 @@ __device__ inline u64 d_huf_read_stats(u8* weights, u64 hwSize, u32* rankStats, 
         }
     } else {                                              // FSE-compressed weights, tableLog <= 6 (:178-183)
         if (iSize + 1 > srcSize) return err(E_SRC_WRONG);
-        short norm[FSE_MAX_SV + 1];
-        u32 dt[1 + 64];
-        u16 cellSym[64];
-        u16 nextOf[FSE_MAX_SV + 1];
-        unsigned tl = 0, msv = FSE_MAX_SV;
-        u64 const h = d_read_ncount(norm, &msv, &tl, in + 1, iSize);
-        if (is_err(h)) return h;
-        if (tl > 6) return err(E_TLOG_TOO_LARGE);
-        u64 const r = d_build_dtable_serial<false>(dt, norm, msv, tl, FSE_MAX_SV, FSE_MAX_TLOG, cellSym, nextOf);
-        if (is_err(r)) return r;
-        oSize = d_fse_decode_serial(weights, hwSize - 1, in + 1 + h, iSize - h, dt);
+        oSize = d_huf_read_weights_fse(weights, hwSize, in, iSize);
         if (is_err(oSize)) return oSize;
     }
     for (unsigned i = 0; i <= HUF_MAX_TLOG; i++) rankStats[i] = 0;
