@@ -242,19 +242,33 @@ fse_decode_cta_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ 
             else { openErr = is_err(e); s1 = (u32)bs_read(bs, tl); bs_refill(bs); }    // fseU16.c:286 ignores the verdict
         }
     }
-    bool const al4 = ((reinterpret_cast<u64>(out) & 3) == 0);
     (void)openErr;
 
-    // physical window: w0 (highest) : w1 : w2, cursor k bits into w0:w1, q = prefetched word below w2, p = address below q
-    u32 w0 = 0, w1 = 0, w2 = 0, q = 0, k = 0; u64 p = 0;
+    // Bit window of the check-free region: a 64-bit shift register hi:lo with `avail` valid bits at the top (the stream is read
+    // downwards: the next bit is bit 31 of hi), q = the next 32-bit word, already loaded, p = the address below q.  A symbol
+    // costs: two table loads, split the cell, take the top nbBits of hi, add, shift the register (2), count -- 11 instructions;
+    // every two symbols a predicated refill (8) appends q when avail <= 32 and requests the next word, whose only reader is the
+    // next refill (this warp issues in order and has nobody to hide behind: the kernel's time is its instruction count times
+    // ~3.3 cycles -- the 96-bit register window with a bit cursor that this replaces took 21 instructions per symbol, a third of
+    // them in its four-register rotation with a 64-bit bounds check).
+    // Addresses: the stream pointer and the output pointer are kept as (low, high) register halves and only the low half moves
+    // -- a predicated 64-bit decrement costs four instructions (add, add-with-carry, two selects), the 32-bit one a single
+    // add.  A block whose compressed slot or output straddles a 4 GiB address boundary takes the exact path instead (sameHi).
+    u32 hi = 0, lo = 0, avail = 0, q = 0, pLo = 0, pHi = 0;        // (pHi:pLo) = address of the next word to request
+    u32 oLo = 0, oHi = 0;
     bool windowed = false;
     auto ldw = [&](u64 a) -> u32 { return a >= lowest ? __ldg(reinterpret_cast<const u32*>(a)) : 0u; };
+    bool const al4 = ((reinterpret_cast<u64>(out) & (WIDE ? 7 : 3)) == 0);   // the check-free loop stores 4 symbols at once
+    bool const sameHi = ((reinterpret_cast<u64>(out) + nBytes) >> 32) == (reinterpret_cast<u64>(out) >> 32)
+                     && ((reinterpret_cast<u64>(cs0) + g.slot + 16) >> 32) == (lowest >> 32);
+    constexpr u32 MARGIN = 24;                                      // container bytes that stay unread below a chunk: the window (8) + q (4)
+                                                                    // + the word in flight (4) + alignment (3) never reach below the stream start
     for (;;) {
         // chunk length: every reload in between must see ptr >= start + 8, every iteration needs 4 output slots
         u32 m = 0;
         if (mode == 0) {
-            if (bs.len >= 8 && bs.at >= 8 && bs.used <= 7) {
-                u64 const ms = (bs.at - 8) / C::WB, mo = (u64)((omax - op) / 4);
+            if (al4 && sameHi && bs.len >= 8 && bs.at >= MARGIN && bs.used <= 7) {
+                u64 const ms = (bs.at - MARGIN) / C::WB, mo = (u64)((omax - op) / 4);
                 m = (u32)(ms < mo ? ms : mo);
             }
             if (m == 0) mode = 1;
@@ -267,52 +281,53 @@ fse_decode_cta_kernel(BatchGeom g, u8* __restrict__ dst, const u8* __restrict__ 
             if (!windowed) {                                        // stand the window on (at, used)
                 u64 const A = reinterpret_cast<u64>(bs.s) + bs.at + 8;
                 u64 const top4 = (A + 3) & ~3ull;
-                k = (u32)(8 * (top4 - A)) + bs.used;               // <= 31
-                w0 = ldw(top4 - 4); w1 = ldw(top4 - 8); w2 = ldw(top4 - 12); q = ldw(top4 - 16); p = top4 - 20;
+                u32 const k = (u32)(8 * (top4 - A)) + bs.used;     // <= 31
+                u32 const w0 = ldw(top4 - 4), w1 = ldw(top4 - 8);
+                hi = __funnelshift_l(w1, w0, k); lo = w1 << k; avail = 64 - k;
+                q = ldw(top4 - 12); pLo = (u32)(top4 - 16); pHi = (u32)((top4 - 16) >> 32);
                 windowed = true;
             }
-            u64 const p0 = p; u32 const k0 = k;
-// window advance, fully predicated: no branch, and the only instruction that reads q is the move that retires the word
-// requested one advance earlier (warps issue in order: anything else touching q would wait for the load in flight)
-#define FSEB_NORM() asm volatile("{\n\t.reg .pred a, g;\n\t" \
-                "setp.ge.u32 a, %4, 32;\n\t" \
-                "setp.ge.u64 g, %5, %6;\n\t" \
-                "and.pred g, g, a;\n\t" \
-                "@a mov.b32 %0, %1;\n\t" \
-                "@a mov.b32 %1, %2;\n\t" \
-                "@a mov.b32 %2, %3;\n\t" \
-                "@a mov.b32 %3, 0;\n\t" \
-                "@g ld.global.nc.u32 %3, [%5];\n\t" \
-                "@a add.u64 %5, %5, -4;\n\t" \
-                "@a add.u32 %4, %4, -32;\n\t}" \
-                : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(q), "+r"(k), "+l"(p) : "l"(lowest) : "memory")
-#define FSEB_PSTEP(ST, SYM, FIRST) do { \
+            u32 const pLo0 = pLo, avail0 = avail;
+            {   u64 const oa = reinterpret_cast<u64>(out) + (u64)op * (WIDE ? 2 : 1); oLo = (u32)oa; oHi = (u32)(oa >> 32); }
+            u32 const oLo0 = oLo;
+#define FSEB_REFILL() asm volatile("{\n\t.reg .pred a;\n\t.reg .b32 t;\n\t.reg .b64 pa;\n\t" \
+                "setp.le.u32 a, %3, 32;\n\t" \
+                "shf.r.clamp.b32 t, %2, 0, %3;\n\t"          /* q >> avail (0 when avail == 32) */ \
+                "@a or.b32 %0, %0, t;\n\t" \
+                "@a shf.r.clamp.b32 %1, 0, %2, %3;\n\t"      /* q << (32 - avail) */ \
+                "@a add.u32 %3, %3, 32;\n\t" \
+                "mov.b64 pa, {%4, %5};\n\t" \
+                "@a ld.global.nc.u32 %2, [pa];\n\t" \
+                "@a add.u32 %4, %4, -4;\n\t}" \
+                : "+r"(hi), "+r"(lo), "+r"(q), "+r"(avail), "+r"(pLo) : "r"(pHi) : "memory")
+#define FSEB_STORE(V0, V1) do { \
+                if (WIDE) asm volatile("{\n\t.reg .b64 oa;\n\tmov.b64 oa, {%0, %1};\n\tst.global.v2.u32 [oa], {%2, %3};\n\t}" :: "r"(oLo), "r"(oHi), "r"(V0), "r"(V1) : "memory"); \
+                else      asm volatile("{\n\t.reg .b64 oa;\n\tmov.b64 oa, {%0, %1};\n\tst.global.u32 [oa], %2;\n\t}" :: "r"(oLo), "r"(oHi), "r"(V0) : "memory"); \
+                oLo += WIDE ? 8 : 4; } while (0)
+#define FSEB_PSTEP(ST, SYM) do { \
                 u32 cell_, nb_, base_; \
                 if (WIDE) { cell_ = lds_u32(tabAddr + 4 * ST); SYM = cell_ >> 20; nb_ = (cell_ >> 16) & 0xF; base_ = cell_ & 0xFFFF; } \
                 else { cell_ = lds_u16(tabAddr + 2 * ST); SYM = lds_u8(symAddr + ST); nb_ = cell_ >> 12; base_ = cell_ & 0xFFF; } \
-                u32 const va_ = __funnelshift_l(w1, w0, k); \
-                u32 const v_ = FIRST ? va_ : (k < 32 ? va_ : __funnelshift_l(w2, w1, k)); \
-                ST = base_ + __funnelshift_l(v_, 0, nb_); k += nb_; } while (0)
+                ST = base_ + __funnelshift_l(hi, 0, nb_); \
+                hi = __funnelshift_l(lo, hi, nb_); lo <<= nb_; avail -= nb_; } while (0)
             #pragma unroll 1
             for (u32 it = 0; it < mm; it++) {
                 u32 a0, a1, a2, a3;
                 if (!WIDE) {
-                    FSEB_PSTEP(s1, a0, true); FSEB_PSTEP(s2, a1, false); FSEB_NORM();
-                    FSEB_PSTEP(s1, a2, true); FSEB_PSTEP(s2, a3, false); FSEB_NORM();
-                    if (al4) *reinterpret_cast<u32*>(out + op) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
-                    else { out[op] = (u8)a0; out[op + 1] = (u8)a1; out[op + 2] = (u8)a2; out[op + 3] = (u8)a3; }
+                    FSEB_PSTEP(s1, a0); FSEB_PSTEP(s2, a1); FSEB_REFILL();
+                    FSEB_PSTEP(s1, a2); FSEB_PSTEP(s2, a3); FSEB_REFILL();
+                    FSEB_STORE(a0 | (a1 << 8) | (a2 << 16) | (a3 << 24), 0u);
                 } else {
-                    FSEB_PSTEP(s1, a0, true); FSEB_PSTEP(s1, a1, false); FSEB_NORM();
-                    FSEB_PSTEP(s1, a2, true); FSEB_PSTEP(s1, a3, false); FSEB_NORM();
-                    u16* const o16 = reinterpret_cast<u16*>(out) + op;
-                    if (al4) { reinterpret_cast<u32*>(o16)[0] = a0 | (a1 << 16); reinterpret_cast<u32*>(o16)[1] = a2 | (a3 << 16); }
-                    else { o16[0] = (u16)a0; o16[1] = (u16)a1; o16[2] = (u16)a2; o16[3] = (u16)a3; }
+                    FSEB_PSTEP(s1, a0); FSEB_PSTEP(s1, a1); FSEB_REFILL();
+                    FSEB_PSTEP(s1, a2); FSEB_PSTEP(s1, a3); FSEB_REFILL();
+                    FSEB_STORE(a0 | (a1 << 16), a2 | (a3 << 16));
                 }
-                op += 4;
             }
+            op += (long long)((oLo - oLo0) / (WIDE ? 2 : 1));
 #undef FSEB_PSTEP
-#undef FSEB_NORM
-            u64 const tot = bs.used + 8 * (p0 - p) + k - k0;       // bits retired in this chunk, carried into the byte-granular counters
+#undef FSEB_REFILL
+#undef FSEB_STORE
+            u64 const tot = (u64)bs.used + 8ull * (pLo0 - pLo) + avail0 - avail;   // (64-bit left to right: avail may exceed avail0)   // bits retired in this chunk, carried into the byte-granular counters
             bs.at -= tot >> 3; bs.used = (unsigned)(tot & 7);
         }
     }
