@@ -236,10 +236,12 @@ huf_plan_kernel(BatchGeom g, u8* __restrict__ cbuf, u64* __restrict__ csizes, co
 // ---------------------------------------------------------------------------------------------
 // kernel 2: emit -- one CTA (4 warps) per block, one warp per stream, no serial section.
 // A stream is the concatenation, last symbol first, of the codes.  The warp walks its segment from the
-// end in groups of 128 symbols: lane l takes the 4 symbols just below hi-4l (coalesced global read,
-// nothing staged), concatenates their codes (<= 48 bits), a warp scan of the lengths gives its bit
-// offset, and it ORs the bits into a circular shared-memory window of the stream (aligned 32-bit words of the
-// destination, whose position is known from the plan); completed words are written out 32 at a time.
+// end, 512 symbols at a time on aligned data: lane l takes the 8 symbols of one 64-bit piece of each of two
+// 256-symbol groups (coalesced global reads, nothing staged), concatenates their codes (<= 88 bits per group),
+// ONE warp scan of the two bit counts (packed in one register) gives both bit offsets, and the lane ORs its bits
+// into a circular shared-memory window of the stream (aligned 32-bit words of the destination, whose position is
+// known from the plan) with four reds at consecutive words; completed words leave 128 at a time, 16 bytes per lane.
+// What bounds it was measured, not assumed: shared-memory wavefronts first (8-byte code cells), the ALU pipe now.
 // ---------------------------------------------------------------------------------------------
 constexpr int THREADS = 128;
 
