@@ -45,3 +45,29 @@ def test_committed_b200_lines_have_the_contract_keys():
         _check_b200_line(d, launches)
         assert d["bit_exact_detail"]["blocks_compared"] == d["bit_exact_detail"]["of_blocks"] == d["config"]["blocks_per_gpu"]
         assert d["bit_exact_detail"]["gpu_decodes_checker_output"] is True
+
+
+def test_committed_multi_gpu_lines_scale_and_carry_the_scatter_gather_object():
+    """round 2's 2-, 4- and 8-GPU lines: weak scaling of the device-timed metric (no data-path collective), the configs[3] object"""
+    one = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_huf_p14_n1.json")))
+    for n in (2, 4, 8):
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_huf_p14_n%d.json" % n)))
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["roundtrip_ok"] is True and not d["clocks"]["reasons"]
+        assert 0.95 * n * one["value"] < d["value"] < 1.05 * n * one["value"]
+        assert d["e2e"]["roundtrip_ok"] is True and d["e2e"]["value"] > one["e2e"]["value"]
+        sg = d["scatter_gather"]
+        assert sg["roundtrip_ok"] is True and sg["pieces"] in (2, 4, 8) and 0 < sg["frac_of_link_bound"] <= 1.0
+        assert sg["bytes_gathered"] == (n - 1) * 2 ** 30 and sg["bytes_scattered"] < 0.6 * sg["bytes_gathered"]    # only used bytes travel
+
+
+def test_docs_quote_the_committed_lines():
+    """README / DESIGN figures are the committed JSON lines' (a stale table is a wrong claim)"""
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    for name in ("r02_bench_huf_p14_n1.json", "r02_bench_fse_p80_n1.json", "r02_bench_u16_p50_n1.json"):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert "%.1f" % d["value"] in readme, (name, d["value"])
+        assert str(d["value"]) in design, (name, d["value"])
+    for n in (2, 4, 8):
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_huf_p14_n%d.json" % n)))
+        assert "%.1f" % d["value"] in readme and str(d["value"]) in design
